@@ -1,0 +1,109 @@
+/*
+ * phnms.h -- C ABI of the B200 (sm_100a) lane-NMS library `libphnms.so`.
+ *
+ * This is the drop-in boundary for PHNet's `libs/ops` lane NMS.  Every entry point takes plain
+ * pointers and sizes (no torch types); device pointers are raw CUDA device addresses and `stream`
+ * is a `cudaStream_t` passed as `void*`.  The library never allocates or frees device memory and
+ * never synchronises the stream: all buffers belong to the caller (PyTorch in the Python mirror,
+ * phnet_b200/ops/nms.py).
+ *
+ * Reference interfaces replaced (paths relative to the PHNet repository):
+ *   libs/ops/nms.py:32-33          nms(boxes, scores, overlap, top_k)
+ *   libs/ops/csrc/nms.cpp:44-61    nms_forward(boxes, scores, thresh, top_k)   [pybind module nms_impl]
+ *   libs/ops/csrc/nms_kernel.cu:147-192  nms_cuda_forward (launcher), :50-96 nms_kernel, :99-143 nms_collect
+ *   libs/ops/csrc/nms.cpp:51       scores.sort(0, true)  (the ordering; see `sort_model`)
+ *
+ * All functions return PHNMS_OK (0), a negative PHNMS_ERR_* code, or a positive `cudaError_t`.
+ * They never throw and keep no global state (re-entrant; any host thread, any stream).
+ */
+#ifndef PHNMS_H_
+#define PHNMS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHNMS_ABI_VERSION 1
+
+#define PHNMS_OK 0
+#define PHNMS_ERR_BAD_ARG (-1)      /* null pointer, negative size, misaligned pointer                         */
+#define PHNMS_ERR_N_OFFSETS (-2)    /* n_off outside [1, 250]   (reference: "Wrong number of offsets", nms_kernel.cu:154) */
+#define PHNMS_ERR_TOO_MANY (-3)     /* ceil(N/64) >= 1000       (reference: MAX_COL_BLOCKS assert, nms_kernel.cu:158)     */
+#define PHNMS_ERR_WORKSPACE (-4)    /* workspace missing or smaller than phnms_workspace_bytes()                */
+#define PHNMS_ERR_DEVICE (-5)       /* current device is not compute capability 10.x                           */
+#define PHNMS_ERR_TUNING (-6)       /* tuning override cannot be honoured (does not fit shared memory)          */
+
+/* sort_model: how ties between equal scores are ordered (libs/ops/csrc/nms.cpp:51 delegates this to
+ * ATen's CUDA sort, which is not a stable sort below 33 elements). */
+#define PHNMS_SORT_TORCH_CUDA 0     /* bit-for-bit what torch 2.11 `scores.sort(0, True)` does on CUDA:
+                                       n<=32 bitonic network, 33..128 stable comparator order, >128 stable radix order */
+#define PHNMS_SORT_STABLE 1         /* stable descending, NaN (either sign) first -- torch.sort(stable=True) semantics */
+#define PHNMS_SORT_STABLE_RADIX 2   /* stable descending by radix bit order (+NaN first, -NaN last)                   */
+
+/* which device algorithm runs */
+#define PHNMS_PATH_AUTO 0
+#define PHNMS_PATH_FUSED 1          /* one cluster of CTAs per frame, proposals resident in shared memory, lazy rows   */
+#define PHNMS_PATH_TILED 2          /* three kernels: radix order -> 64x64 tile bitmask -> warp-ballot greedy scan     */
+
+typedef struct phnms_tuning {
+    int path;            /* PHNMS_PATH_*                                             (0 = auto) */
+    int cluster;         /* CTAs per frame for the fused path: 1,2,4,8,16            (0 = auto) */
+    int threads;         /* threads per CTA for the fused path: multiple of 32, <=512 (0 = auto) */
+    int max_clusters;    /* cap on resident clusters (persistent grid size)          (0 = auto) */
+} phnms_tuning;
+
+typedef struct phnms_plan {
+    int path;            /* PHNMS_PATH_FUSED or PHNMS_PATH_TILED */
+    int cluster;         /* CTAs per frame (fused) */
+    int threads;         /* threads per CTA */
+    int rows_per_cta;    /* proposals resident per CTA (fused) */
+    int smem_bytes;      /* dynamic shared memory per CTA */
+    int grid;            /* CTAs launched */
+    int launches;        /* kernel launches one phnms_forward_f32 call makes */
+    size_t workspace_bytes;
+} phnms_plan;
+
+int phnms_abi_version(void);
+const char *phnms_error_string(int code);
+
+/* Bytes of device workspace `phnms_forward_f32` needs for this shape (0 for the fused path). */
+size_t phnms_workspace_bytes(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning /* nullable */);
+
+/* Fills `plan` with what phnms_forward_f32 would launch for this shape on the current device. */
+int phnms_plan_query(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning /* nullable */, phnms_plan *plan);
+
+/*
+ * Lane NMS over a batch of F independent frames (F = 1 is exactly one reference `nms` call).
+ *
+ *   props    [F, N, 5+n_off] fp32, contiguous, device.  Row = (logit0, logit1, start_y, start_x, length, x_0..x_{n_off-1})
+ *                                                        as produced by get_lanes (libs/models/Router4OL.py:454-458)
+ *   scores   [F, N] fp32, contiguous, device
+ *   n_valid  [F] int32 device, nullable: frame f uses only its first n_valid[f] rows (NULL = all N)
+ *   thresh   `overlap` of the reference call (pixels of mean |dx|); top_k as in the reference (0 = never stop early)
+ *   keep     [F, N] int64 device: kept ORIGINAL proposal indices in score order, zero padded        (nms_kernel.cu:118,139-140)
+ *   num_keep [F]    int64 device: min(top_k, number kept)                                         (nms_kernel.cu:142)
+ *   parent   [F, N] int64 device: 1-based slot of the last kept lane covering each proposal, 0 = none (nms_kernel.cu:123-129)
+ *   ws       device workspace of at least phnms_workspace_bytes() bytes (may be NULL when that is 0)
+ *   stream   cudaStream_t on which everything is enqueued; the call is asynchronous
+ */
+int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
+                      int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
+                      int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning /* nullable */,
+                      void *stream);
+
+/*
+ * The ordering alone (libs/ops/csrc/nms.cpp:51): order[f, i] = original index of the i-th proposal of frame f
+ * in descending score order under `sort_model`; entries beyond n_valid[f] are zero.
+ * `ws` must hold phnms_order_workspace_bytes(F, N) bytes.
+ */
+size_t phnms_order_workspace_bytes(int64_t F, int64_t N);
+int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int sort_model,
+                    int64_t *order, void *ws, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHNMS_H_ */

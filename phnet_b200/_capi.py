@@ -1,0 +1,88 @@
+"""ctypes binding of libphnms.so (include/phnms.h).  Fails loudly: there is no CPU or PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "csrc", "libphnms.so")
+
+PATH_AUTO, PATH_FUSED, PATH_TILED = 0, 1, 2
+SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
+
+EXPORTS = (
+    "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query",
+    "phnms_forward_f32", "phnms_order_workspace_bytes", "phnms_order_f32",
+)
+
+
+class Tuning(ctypes.Structure):
+    _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
+                ("max_clusters", ctypes.c_int)]
+
+
+class Plan(ctypes.Structure):
+    _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
+                ("rows_per_cta", ctypes.c_int), ("smem_bytes", ctypes.c_int), ("grid", ctypes.c_int),
+                ("launches", ctypes.c_int), ("workspace_bytes", ctypes.c_size_t)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class PhnmsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"phnms: {msg} (code {code})")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the native library, building it first if the sources are newer and nvcc is present."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing and could not be built; the lane-NMS op has no fallback path")
+    L = ctypes.CDLL(SO_PATH)
+    vp, i64, ci, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
+    L.phnms_abi_version.restype = ci
+    L.phnms_error_string.argtypes = [ci]
+    L.phnms_error_string.restype = ctypes.c_char_p
+    L.phnms_workspace_bytes.argtypes = [i64, i64, ci, ctypes.POINTER(Tuning)]
+    L.phnms_workspace_bytes.restype = sz
+    L.phnms_plan_query.argtypes = [i64, i64, ci, ctypes.POINTER(Tuning), ctypes.POINTER(Plan)]
+    L.phnms_plan_query.restype = ci
+    L.phnms_forward_f32.argtypes = [vp, vp, vp, i64, i64, ci, ctypes.c_float, i64, ci, vp, vp, vp, vp, sz,
+                                    ctypes.POINTER(Tuning), vp]
+    L.phnms_forward_f32.restype = ci
+    L.phnms_order_workspace_bytes.argtypes = [i64, i64]
+    L.phnms_order_workspace_bytes.restype = sz
+    L.phnms_order_f32.argtypes = [vp, vp, i64, i64, ci, vp, vp, sz, vp]
+    L.phnms_order_f32.restype = ci
+    if L.phnms_abi_version() != 1:
+        raise ImportError("libphnms.so ABI version mismatch; rebuild with `python -m phnet_b200.build`")
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise PhnmsError(code, lib().phnms_error_string(code).decode())
+
+
+def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0):
+    if not (path or cluster or threads or max_clusters):
+        return None
+    return Tuning(path, cluster, threads, max_clusters)
+
+
+def plan(F: int, N: int, n_off: int, tune: Tuning | None = None) -> dict:
+    p = Plan()
+    check(lib().phnms_plan_query(F, N, n_off, ctypes.byref(tune) if tune else None, ctypes.byref(p)))
+    return p.as_dict()

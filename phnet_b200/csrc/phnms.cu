@@ -1,0 +1,272 @@
+// phnms.cu -- C ABI (include/phnms.h) and launch planning for the B200 lane-NMS library.
+//
+// Built with:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// No torch, no ATen: the Python mirror (phnet_b200/ops/nms.py) passes raw device pointers and a stream.
+#include "../../include/phnms.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "fused_nms.cuh"
+#include "tiled_nms.cuh"
+
+using namespace phnms;
+
+namespace {
+
+struct DeviceInfo {
+    int sms;
+    int smem_optin;  // max dynamic shared memory per CTA
+    int cc_major;
+};
+
+int device_info(DeviceInfo *d) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    e = cudaDeviceGetAttribute(&d->cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    return (int)e;
+}
+
+int check_shape(int64_t F, int64_t N, int n_off) {
+    if (F < 0 || N < 0) return PHNMS_ERR_BAD_ARG;
+    if (n_off < 1 || n_off > 250) return PHNMS_ERR_N_OFFSETS;
+    if ((N + 63) / 64 >= 1000) return PHNMS_ERR_TOO_MANY;  // nms_kernel.cu:158
+    return PHNMS_OK;
+}
+
+size_t tiled_workspace(int64_t F, int64_t N) {
+    const size_t cb = (size_t)((N + 63) / 64);
+    // order (i64) + radix ping-pong (4 x u32) + bitmask
+    return (size_t)F * N * 8 + (size_t)F * N * 16 + (size_t)F * N * cb * 8 + 256;
+}
+
+// Decide what to launch.  No device queries when `dev` is null (shape-only planning with B200 constants).
+int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const DeviceInfo *dev, phnms_plan *pl) {
+    const int P = 5 + n_off;
+    const int smem_max = dev ? dev->smem_optin : 232448;
+    const int sms = dev ? dev->sms : 148;
+    phnms_tuning t = {0, 0, 0, 0};
+    if (tun) t = *tun;
+    pl->workspace_bytes = 0;
+    pl->launches = 1;
+
+    auto fits = [&](int c, FusedLayout *L, int *rpc) {
+        int r = (int)((N + c - 1) / c);
+        if (r < 32) r = 32;  // a frame of <= 32 proposals lives in one CTA (bitonic replay needs all of them)
+        *rpc = r;
+        *L = fused_layout(r, P, c);
+        return L->total <= smem_max;
+    };
+
+    int csize = 0, rpc = 0;
+    FusedLayout L;
+    if (t.path != PHNMS_PATH_TILED) {
+        if (t.cluster) {
+            const int c = t.cluster;
+            if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 16)) return PHNMS_ERR_TUNING;
+            if (!fits(c, &L, &rpc)) return PHNMS_ERR_TUNING;
+            csize = c;
+        } else {
+            // smallest cluster that leaves room for two CTAs per SM (load of one frame overlaps compute of another),
+            // else the smallest that fits at all
+            const int cand[5] = {1, 2, 4, 8, 16};
+            for (int i = 0; i < 4 && !csize; ++i)
+                if (fits(cand[i], &L, &rpc) && L.total <= smem_max / 2 - 1024) csize = cand[i];
+            for (int i = 0; i < 5 && !csize; ++i)
+                if (fits(cand[i], &L, &rpc)) csize = cand[i];
+        }
+        if (!csize && t.path == PHNMS_PATH_FUSED) return PHNMS_ERR_TUNING;
+    }
+
+    if (csize) {
+        fits(csize, &L, &rpc);
+        int threads = t.threads ? t.threads : round_up(rpc, 32);
+        if (threads > 512) threads = 512;
+        if (threads < 128) threads = 128;
+        if (threads % 32) return PHNMS_ERR_TUNING;
+        int per_sm = smem_max / (L.total + 1024);
+        if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 32) per_sm = 32;
+        long long resident = (long long)(sms / csize) * per_sm;
+        if (resident < 1) resident = 1;
+        if (t.max_clusters > 0 && resident > t.max_clusters) resident = t.max_clusters;
+        long long clusters = F < resident ? F : resident;
+        if (clusters < 1) clusters = 1;
+        pl->path = PHNMS_PATH_FUSED;
+        pl->cluster = csize;
+        pl->threads = threads;
+        pl->rows_per_cta = rpc;
+        pl->smem_bytes = L.total;
+        pl->grid = (int)(clusters * csize);
+        return PHNMS_OK;
+    }
+
+    pl->path = PHNMS_PATH_TILED;
+    pl->cluster = 1;
+    pl->threads = kMaskThreads;
+    pl->rows_per_cta = kTile;
+    pl->smem_bytes = 2 * kTile * ((((P + 3) & ~3) + 1) * 4 + 8);
+    const long long cb = (N + 63) / 64;
+    pl->grid = (int)(cb * (cb + 1) / 2);
+    pl->launches = 3;
+    pl->workspace_bytes = tiled_workspace(F, N);
+    return PHNMS_OK;
+}
+
+int launch_fused(const phnms_plan &pl, const FusedParams &fp, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(phnms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (pl.cluster > 8) {
+        e = cudaFuncSetAttribute(phnms_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3((unsigned)pl.threads);
+    cfg.dynamicSmemBytes = (size_t)pl.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pl.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, phnms_fused_kernel, fp);
+    return (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int phnms_abi_version(void) { return PHNMS_ABI_VERSION; }
+
+const char *phnms_error_string(int code) {
+    switch (code) {
+        case PHNMS_OK: return "ok";
+        case PHNMS_ERR_BAD_ARG: return "bad argument (null pointer, negative size or misaligned pointer)";
+        case PHNMS_ERR_N_OFFSETS: return "Wrong number of offsets: n_off must be in [1, 250]";
+        case PHNMS_ERR_TOO_MANY: return "The number of column blocks must be less than MAX_COL_BLOCKS (ceil(N/64) < 1000)";
+        case PHNMS_ERR_WORKSPACE: return "workspace missing or too small (see phnms_workspace_bytes)";
+        case PHNMS_ERR_DEVICE: return "current CUDA device is not compute capability 10.x (library is sm_100a only)";
+        case PHNMS_ERR_TUNING: return "tuning override cannot be honoured for this shape";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+size_t phnms_workspace_bytes(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning) {
+    phnms_plan pl;
+    if (check_shape(F, N, n_off) != PHNMS_OK) return 0;
+    if (make_plan(F, N, n_off, tuning, nullptr, &pl) != PHNMS_OK) return 0;
+    return pl.workspace_bytes;
+}
+
+int phnms_plan_query(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning, phnms_plan *plan) {
+    if (!plan) return PHNMS_ERR_BAD_ARG;
+    int rc = check_shape(F, N, n_off);
+    if (rc != PHNMS_OK) return rc;
+    DeviceInfo dev;
+    const bool have_dev = device_info(&dev) == 0;
+    return make_plan(F, N, n_off, tuning, have_dev ? &dev : nullptr, plan);
+}
+
+size_t phnms_order_workspace_bytes(int64_t F, int64_t N) {
+    if (F < 0 || N < 0) return 0;
+    return (size_t)F * N * 16 + 256;
+}
+
+int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int sort_model, int64_t *order,
+                    void *ws, size_t ws_bytes, void *stream) {
+    if (F < 0 || N < 0 || sort_model < 0 || sort_model > 2) return PHNMS_ERR_BAD_ARG;
+    if (F == 0 || N == 0) return PHNMS_OK;
+    if (!scores || !order) return PHNMS_ERR_BAD_ARG;
+    if (N > 0x7fffffff / 8) return PHNMS_ERR_TOO_MANY;
+    if (!ws || ws_bytes < phnms_order_workspace_bytes(F, N)) return PHNMS_ERR_WORKSPACE;
+    uint32_t *w = reinterpret_cast<uint32_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    phnms_order_kernel<<<(unsigned)F, kOrderThreads, 0, (cudaStream_t)stream>>>(
+        scores, n_valid, (int)N, sort_model, reinterpret_cast<long long *>(order), w);
+    return (int)cudaGetLastError();
+}
+
+int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
+                      float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
+                      void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_) {
+    int rc = check_shape(F, N, n_off);
+    if (rc != PHNMS_OK) return rc;
+    if (sort_model < 0 || sort_model > 2 || top_k < 0) return PHNMS_ERR_BAD_ARG;
+    if (F == 0) return PHNMS_OK;
+    if (!num_keep) return PHNMS_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N == 0) return (int)cudaMemsetAsync(num_keep, 0, (size_t)F * 8, stream);
+    if (!props || !scores || !keep || !parent) return PHNMS_ERR_BAD_ARG;
+    if (((uintptr_t)props | (uintptr_t)scores) & 3u) return PHNMS_ERR_BAD_ARG;
+    if (((uintptr_t)keep | (uintptr_t)parent | (uintptr_t)num_keep) & 7u) return PHNMS_ERR_BAD_ARG;
+
+    DeviceInfo dev;
+    rc = device_info(&dev);
+    if (rc != 0) return rc;
+    if (dev.cc_major != 10) return PHNMS_ERR_DEVICE;
+    phnms_plan pl;
+    rc = make_plan(F, N, n_off, tuning, &dev, &pl);
+    if (rc != PHNMS_OK) return rc;
+
+    if (pl.path == PHNMS_PATH_FUSED) {
+        FusedParams fp;
+        fp.props = props;
+        fp.scores = scores;
+        fp.n_valid = n_valid;
+        fp.keep = reinterpret_cast<long long *>(keep);
+        fp.num_keep = reinterpret_cast<long long *>(num_keep);
+        fp.parent = reinterpret_cast<long long *>(parent);
+        fp.F = F;
+        fp.top_k = top_k;
+        fp.N = (int)N;
+        fp.n_off = n_off;
+        fp.rpc = pl.rows_per_cta;
+        fp.csize = pl.cluster;
+        fp.sort_model = sort_model;
+        fp.thr = thresh;
+        fp.L = fused_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
+        return launch_fused(pl, fp, stream);
+    }
+
+    // ---- tiled path: order -> bitmask -> scan ------------------------------------------------------------
+    if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    long long *order = reinterpret_cast<long long *>(base);
+    uint32_t *sort_ws = reinterpret_cast<uint32_t *>(base + (size_t)F * N * 8);
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(base + (size_t)F * N * 24);
+    const int col_blocks = (int)((N + 63) / 64);
+    const int P = 5 + n_off;
+
+    phnms_order_kernel<<<(unsigned)F, kOrderThreads, 0, stream>>>(scores, n_valid, (int)N, sort_model, order, sort_ws);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+
+    e = cudaFuncSetAttribute(phnms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    // gridDim.y is limited to 65535 frames per launch
+    for (int64_t f0 = 0; f0 < F; f0 += 65535) {
+        const int64_t fc = (F - f0) < 65535 ? (F - f0) : 65535;
+        dim3 grid((unsigned)pl.grid, (unsigned)fc);
+        phnms_mask_kernel<<<grid, kMaskThreads, (size_t)pl.smem_bytes, stream>>>(
+            props + (size_t)f0 * N * P, order + (size_t)f0 * N, n_valid ? n_valid + f0 : nullptr, (int)N, n_off, thresh,
+            col_blocks, mask + (size_t)f0 * N * col_blocks, props + (size_t)F * N * P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    phnms_scan_kernel<<<(unsigned)F, 32, 0, stream>>>(order, mask, n_valid, (int)N, col_blocks, top_k,
+                                                      reinterpret_cast<long long *>(keep),
+                                                      reinterpret_cast<long long *>(num_keep),
+                                                      reinterpret_cast<long long *>(parent));
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+"""Host-side mirror of PHNet's `libs/ops` lane NMS, backed by libphnms.so (hand-written sm_100a CUDA).
+
+Reference interface mirrored (paths relative to the PHNet repo):
+    libs/ops/nms.py:32-33          def nms(boxes, scores, overlap, top_k)
+    libs/ops/csrc/nms.cpp:44-57    nms_forward: sort scores descending, CUDA + contiguity checks
+    libs/ops/csrc/nms_kernel.cu:147-192  nms_cuda_forward: shape checks, outputs keep / num_to_keep / parent_object_index
+Callers: the five `get_lanes` copies (libs/models/Router4OL.py:460-465 and siblings) do
+
+    keep, num_to_keep, _ = nms(nms_predictions, scores, overlap=nms_thres, top_k=nms_topk)
+    keep = keep[:num_to_keep]
+
+so the keyword names `overlap` / `top_k`, the list-of-three return value, int64 dtype, CUDA device, the 0-dim
+`num_to_keep` and the zero padding of `keep` are all part of the contract kept here.
+
+PyTorch is used for device memory and the current stream only; there is no fallback: if the native library
+cannot be loaded, or the tensors are not on a CUDA device, the op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _capi
+
+__all__ = ["nms", "nms_batched", "sort_order", "plan"]
+
+
+def _check_inputs(boxes: torch.Tensor, scores: torch.Tensor, batched: bool):
+    # error behaviour of the reference: CHECK_CUDA / CHECK_CONTIGUOUS (nms.cpp:40-42,53-54; nms_kernel.cu:167),
+    # AT_DISPATCH_FLOATING_TYPES (nms_kernel.cu:171), row-width check (:154)
+    if not isinstance(boxes, torch.Tensor) or not isinstance(scores, torch.Tensor):
+        raise TypeError("nms: boxes and scores must be torch tensors")
+    if not boxes.is_cuda:
+        raise RuntimeError("boxes must be a CUDA tensor")
+    if not scores.is_cuda:
+        raise RuntimeError("scores must be a CUDA tensor")
+    if scores.device != boxes.device:
+        raise RuntimeError("boxes and scores must be on the same device")
+    if not boxes.is_contiguous():
+        raise RuntimeError("boxes must be contiguous")
+    if boxes.dtype != torch.float32:
+        raise RuntimeError(f"nms_cuda_forward not implemented for '{boxes.dtype}' (this build computes in float32 only)")
+    want = 3 if batched else 2
+    if boxes.dim() != want:
+        raise RuntimeError(f"boxes must have {want} dimensions, got {boxes.dim()}")
+    if boxes.shape[-1] < 6:
+        raise RuntimeError("Wrong number of offsets. Rows are 5 + n_offsets wide")
+    if scores.dtype != torch.float32:
+        scores = scores.float()          # the reference sorts whatever dtype it is given; order is unchanged
+    if not scores.is_contiguous():
+        scores = scores.contiguous()     # `scores.sort` accepts strided input (nms.cpp:51)
+    if scores.shape != boxes.shape[:-1]:
+        raise RuntimeError("scores must have one entry per proposal")
+    return boxes, scores
+
+
+def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tune, keep, num, parent):
+    top_k = int(top_k)
+    if top_k < 0:
+        raise TypeError("top_k must be non-negative (unsigned long in the reference, nms.cpp:48)")
+    L = _capi.lib()
+    t = tune if isinstance(tune, _capi.Tuning) or tune is None else _capi.tuning(**tune)
+    tp = ctypes.byref(t) if t is not None else None
+    ws_bytes = L.phnms_workspace_bytes(F, N, n_off, tp)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=boxes.device) if ws_bytes else None
+    with torch.cuda.device(boxes.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = L.phnms_forward_f32(boxes.data_ptr(), scores.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
+                                 F, N, n_off, float(overlap), top_k, int(sort_model), keep.data_ptr(), num.data_ptr(),
+                                 parent.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, tp, stream)
+    _capi.check(rc)
+    if ws is not None:
+        ws.record_stream(torch.cuda.current_stream(boxes.device))
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model: int = _capi.SORT_TORCH_CUDA,
+        tuning=None):
+    """Drop-in for `libs.ops.nms` (libs/ops/nms.py:32).
+
+    boxes  [N, 5+n_off] fp32 CUDA contiguous; scores [N]; overlap: pixel threshold; top_k: stop after this many lanes.
+    Returns [keep[N] int64, num_to_keep[] int64, parent_object_index[N] int64] on the same device.
+    """
+    boxes, scores = _check_inputs(boxes, scores, batched=False)
+    N, P = boxes.shape
+    dev = boxes.device
+    keep = torch.empty(N, dtype=torch.int64, device=dev)
+    parent = torch.empty(N, dtype=torch.int64, device=dev)
+    num = torch.empty((), dtype=torch.int64, device=dev)
+    _launch(boxes, scores, None, 1, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent)
+    return [keep, num, parent]
+
+
+def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, n_valid: torch.Tensor | None = None, *,
+                sort_model: int = _capi.SORT_TORCH_CUDA, tuning=None, out=None):
+    """F independent `nms` calls in one launch.
+
+    boxes [F, N, 5+n_off], scores [F, N], n_valid [F] int32 (optional: real proposals per frame, rest is padding).
+    Returns (keep[F, N], num_to_keep[F], parent_object_index[F, N]); frame f equals
+    `nms(boxes[f, :n_valid[f]], scores[f, :n_valid[f]], overlap, top_k)` padded with zeros to N.
+    """
+    boxes, scores = _check_inputs(boxes, scores, batched=True)
+    F, N, P = boxes.shape
+    dev = boxes.device
+    if n_valid is not None:
+        if n_valid.device != dev or n_valid.dtype != torch.int32 or n_valid.shape != (F,) or not n_valid.is_contiguous():
+            raise RuntimeError("n_valid must be a contiguous int32 tensor of shape [F] on the same device")
+    if out is None:
+        keep = torch.empty((F, N), dtype=torch.int64, device=dev)
+        num = torch.empty((F,), dtype=torch.int64, device=dev)
+        parent = torch.empty((F, N), dtype=torch.int64, device=dev)
+    else:
+        keep, num, parent = out
+    _launch(boxes, scores, n_valid, F, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent)
+    return keep, num, parent
+
+
+def sort_order(scores: torch.Tensor, n_valid: torch.Tensor | None = None, *, sort_model: int = _capi.SORT_TORCH_CUDA):
+    """The ordering step alone: `scores.sort(0, True)[1]` of libs/ops/csrc/nms.cpp:51, per frame.  scores [F, N] or [N]."""
+    if not scores.is_cuda:
+        raise RuntimeError("scores must be a CUDA tensor")
+    one = scores.dim() == 1
+    s = scores.reshape(1, -1) if one else scores
+    s = s.contiguous().float()
+    F, N = s.shape
+    L = _capi.lib()
+    order = torch.zeros((F, N), dtype=torch.int64, device=s.device)
+    ws_bytes = L.phnms_order_workspace_bytes(F, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
+    with torch.cuda.device(s.device):
+        rc = L.phnms_order_f32(s.data_ptr(), n_valid.data_ptr() if n_valid is not None else None, F, N, int(sort_model),
+                               order.data_ptr(), ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream)
+    _capi.check(rc)
+    ws.record_stream(torch.cuda.current_stream(s.device))
+    return order[0] if one else order
+
+
+def plan(F: int, N: int, n_off: int, tuning=None) -> dict:
+    """What one call would launch for this shape (path, cluster size, threads, shared memory, grid)."""
+    t = tuning if isinstance(tuning, _capi.Tuning) or tuning is None else _capi.tuning(**tuning)
+    return _capi.plan(F, N, n_off, t)
