@@ -38,10 +38,11 @@ extern "C" {
 
 /* sort_model: how ties between equal scores are ordered (libs/ops/csrc/nms.cpp:51 delegates this to
  * ATen's CUDA sort, which is not a stable sort below 33 elements). */
-#define PHNMS_SORT_TORCH_CUDA 0     /* bit-for-bit what torch 2.11 `scores.sort(0, True)` does on CUDA:
-                                       n<=32 bitonic network, 33..128 stable comparator order, >128 stable radix order */
-#define PHNMS_SORT_STABLE 1         /* stable descending, NaN (either sign) first -- torch.sort(stable=True) semantics */
-#define PHNMS_SORT_STABLE_RADIX 2   /* stable descending by radix bit order (+NaN first, -NaN last)                   */
+#define PHNMS_SORT_TORCH_CUDA 0     /* bit-for-bit what torch 2.11 `scores.sort(0, True)` does on CUDA (measured on B200,
+                                       tests/golden/torch_cuda_sort.npz): n<=32 ATen's unstable bitonic network,
+                                       n>32 stable radix bit order (+NaN first, -NaN last, -0.0 == +0.0)               */
+#define PHNMS_SORT_STABLE 1         /* stable descending, NaN of either sign first (torch CPU / numpy semantics)       */
+#define PHNMS_SORT_STABLE_RADIX 2   /* stable radix bit order for every n == torch.sort(stable=True) on CUDA          */
 
 /* which device algorithm runs */
 #define PHNMS_PATH_AUTO 0

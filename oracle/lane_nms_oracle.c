@@ -22,7 +22,9 @@
  * tests/golden/make_ref_fixtures.py).
  *
  * GPU arithmetic that has to be emulated on x86 (from the PTX of the reference build):
- *   (int)(double)      -> cvt.rzi.s32.f64 : truncates toward zero, SATURATES, NaN -> 0
+ *   (int)(double)      -> F2I.F64.TRUNC   : truncates toward zero, SATURATES, NaN -> 0x80000000 (INT_MIN).
+ *                         (PTX documents NaN -> 0 for cvt; the B200 measurably returns INT_MIN for the f64 source:
+ *                          the live reference op only matches this restatement with INT_MIN, see tests/golden.)
  *   int add/sub        -> wraps (two's complement)
  *   unsigned char i    -> (5 + start) & 255
  *   float accumulation -> sequential fp32 adds in ascending offset order, no FMA
@@ -41,7 +43,7 @@
 
 /* ---- GPU integer conversion: cvt.rzi.s32.f64 -------------------------------------- */
 static int32_t cvt_rzi_s32_f64(double d) {
-    if (d != d) return 0;
+    if (d != d) return INT32_MIN; /* measured on B200: F2I.F64.TRUNC(NaN) = 0x80000000 (tests/golden) */
     if (d >= 2147483647.0) return INT32_MAX;
     if (d <= -2147483648.0) return INT32_MIN;
     return (int32_t)d;
@@ -135,9 +137,10 @@ static int cmp_u64(const void *x, const void *y) {
     return (a > b) - (a < b);
 }
 
-/* sort_model: 0 = torch CUDA (n<=32 bitonic, 33..128 merge/comparator, >128 radix)
- *             1 = always stable comparator order (== torch.sort(stable=True) on CUDA for n<=128)
- *             2 = always stable radix order */
+/* sort_model: 0 = torch 2.11 CUDA `sort(0, True)`: n<=32 unstable bitonic network, n>32 stable radix bit order
+ *                 (pinned by tests/golden/torch_cuda_sort.npz, generated on a B200)
+ *             1 = stable, comparator order: NaN of either sign first (torch CPU / numpy semantics)
+ *             2 = stable radix bit order for every n (== torch.sort(stable=True) on CUDA): +NaN first, -NaN last */
 void phoracle_order(const float *scores, int64_t n, int64_t *order, int sort_model) {
     if (n <= 0) return;
     if (n == 1) { order[0] = 0; return; }
@@ -177,7 +180,7 @@ void phoracle_order(const float *scores, int64_t n, int64_t *order, int sort_mod
         for (int64_t i = 0; i < n; ++i) order[i] = vals[i];
         return;
     }
-    int mode = (sort_model == 2 || (sort_model == 0 && n > 128)) ? 1 : 0;
+    int mode = (sort_model == 1) ? 0 : 1;
     uint64_t *tmp = (uint64_t *)malloc((size_t)n * sizeof(uint64_t));
     for (int64_t i = 0; i < n; ++i)
         tmp[i] = ((uint64_t)phoracle_key_desc(scores[i], mode) << 32) | (uint64_t)(uint32_t)i;

@@ -21,9 +21,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(HERE, "liblane_nms_oracle.so")
 
 # sort models (see phoracle_order)
-SORT_TORCH_CUDA = 0      # what `scores.sort(0, True)` does on CUDA in torch 2.11 (n<=32 bitonic, ...)
-SORT_STABLE_CMP = 1      # stable, comparator order (NaN of any sign first)
-SORT_STABLE_RADIX = 2    # stable, radix bit order (+NaN first, -NaN last)
+SORT_TORCH_CUDA = 0      # what `scores.sort(0, True)` does on CUDA in torch 2.11 (n<=32 bitonic, else stable radix)
+SORT_STABLE_CMP = 1      # stable, comparator order (NaN of any sign first; torch CPU semantics)
+SORT_STABLE_RADIX = 2    # stable, radix bit order (+NaN first, -NaN last) == torch.sort(stable=True) on CUDA
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 _i64p = ctypes.POINTER(ctypes.c_int64)
@@ -143,7 +143,7 @@ def nms_batched(props, scores, n_valid, thr: float, top_k: int, sort_model: int 
 # ---------------------------------------------------------------------------------------------
 def _cvt_rzi(d: float) -> int:
     if d != d:
-        return 0
+        return -2147483648  # B200 F2I.F64.TRUNC(NaN) = INT_MIN (pinned by tests/golden)
     if d >= 2147483647.0:
         return 2147483647
     if d <= -2147483648.0:

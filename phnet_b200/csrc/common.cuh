@@ -2,7 +2,7 @@
 //
 // Arithmetic contract (bit-exactness with PHNet libs/ops/csrc/nms_kernel.cu:26-48, `devIoU`):
 //   * every fp32 op is an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn): never contracted to FMA
-//   * (int)(double) is cvt.rzi.s32.f64: truncating, saturating, NaN -> 0 (what the reference compiles to)
+//   * (int)(double) is F2I.F64.TRUNC: truncating, saturating, NaN -> INT_MIN on B200 (what the reference compiles to)
 //   * int arithmetic wraps; the offset loop counter is an `unsigned char` in the reference (:38)
 #pragma once
 #include <cuda_runtime.h>

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(512, 1) phnms_fused_kernel(const FusedParams p
 
         // ---- rank keys from scores (global loads overlap the bulk copy) ----------------------------------------
         const bool bitonic = (p.sort_model == 0) && nv <= 32 && nv >= 2;  // torch: unstable bitonic network (n <= 32)
-        const bool nan_first = (p.sort_model == 1) || (p.sort_model == 0 && nv <= 128);
+        const bool nan_first = p.sort_model == 1;
         const float *sc = p.scores + (size_t)f * p.N + r0;
         for (int c = tid; c < nloc; c += T) {
             if (!bitonic) colkey[c] = key_desc(sc[c], nan_first);

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kOrderThreads) phnms_order_kernel(const float 
         return;
     }
 
-    const bool nan_first = (sort_model == 1) || (sort_model == 0 && n <= 128);
+    const bool nan_first = sort_model == 1;
     uint32_t *k0 = ws + (size_t)f * 4 * N, *k1 = k0 + N, *v0 = k1 + N, *v1 = v0 + N;
     for (int i = tid; i < n; i += kOrderThreads) {
         k0[i] = key_desc(sc[i], nan_first);

@@ -75,7 +75,7 @@ def main(out_dir):
                 s[torch.randint(0, N, (max(1, N // 12),), generator=g)] = neg_nan
                 s[torch.randint(0, N, (max(1, N // 8),), generator=g)] *= -1.0
             order = torch.sort(s.to(dev), 0, True)[1].cpu()
-            order_stable = torch.sort(s.to(dev), 0, True, stable=True)[1].cpu()
+            order_stable = torch.sort(s.to(dev), dim=0, descending=True, stable=True)[1].cpu()
             sort_blob[f"N{N}_v{variant}/scores_bits"] = s.view(torch.int32).numpy()
             sort_blob[f"N{N}_v{variant}/order"] = order.numpy()
             sort_blob[f"N{N}_v{variant}/order_stable"] = order_stable.numpy()

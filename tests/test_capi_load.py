@@ -1,0 +1,91 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol include/phnms.h declares,
+plans launches sensibly and rejects bad arguments before touching a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from phnet_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "phnms.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(phnms_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    syms = declared_symbols()
+    assert set(syms) == set(_capi.EXPORTS), "include/phnms.h and the ctypes binding disagree"
+    for s in syms:
+        assert hasattr(L, s), f"libphnms.so does not export {s}"
+    assert L.phnms_abi_version() == 1
+
+
+def test_library_is_sm100a_only_and_has_tma_and_cluster_code():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _capi.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    sass = subprocess.run(["cuobjdump", "-sass", _capi.SO_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA 1-D bulk copy)
+    assert "UCGABAR" in sass         # barrier.cluster
+    assert "FFMA" not in sass        # the fp32 predicate must never be contracted
+
+
+def test_error_strings_and_argument_checks_without_a_gpu():
+    L = _capi.lib()
+    assert b"offsets" in L.phnms_error_string(-2)
+    assert b"MAX_COL_BLOCKS" in L.phnms_error_string(-3)
+    nul = None
+    # shape errors are detected before any CUDA call
+    assert L.phnms_forward_f32(nul, nul, nul, 1, 10, 0, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == -2
+    assert L.phnms_forward_f32(nul, nul, nul, 1, 10, 251, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == -2
+    assert L.phnms_forward_f32(nul, nul, nul, 1, 64000, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == -3
+    assert L.phnms_forward_f32(nul, nul, nul, -1, 10, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == -1
+    assert L.phnms_forward_f32(nul, nul, nul, 1, 10, 72, 50.0, -4, 0, nul, nul, nul, nul, 0, None, nul) == -1
+    assert L.phnms_forward_f32(nul, nul, nul, 1, 10, 72, 50.0, 4, 7, nul, nul, nul, nul, 0, None, nul) == -1
+    assert L.phnms_forward_f32(nul, nul, nul, 0, 10, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == 0   # F == 0
+    assert L.phnms_forward_f32(nul, nul, nul, 1, 10, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == -1  # null outputs
+    assert L.phnms_order_f32(nul, nul, 1, 10, 0, nul, nul, 0, nul) == -1
+    with pytest.raises(_capi.PhnmsError):
+        _capi.check(-6)
+
+
+def test_plans():
+    p = _capi.plan(16384, 1000, 72)
+    assert p["path"] == _capi.PATH_FUSED and p["cluster"] * p["rows_per_cta"] >= 1000
+    assert p["smem_bytes"] <= 232448 and p["grid"] % p["cluster"] == 0 and p["launches"] == 1
+    assert p["workspace_bytes"] == 0
+    assert _capi.plan(1, 240, 72)["cluster"] == 1                       # the real OpenLane-V shape fits one CTA
+    assert _capi.plan(1, 8192, 72)["path"] == _capi.PATH_FUSED          # the whole stress sweep stays on the fused path
+    big = _capi.plan(1, 40000, 72)
+    assert big["path"] == _capi.PATH_TILED and big["launches"] == 3 and big["workspace_bytes"] > 0
+    assert _capi.lib().phnms_workspace_bytes(1, 40000, 72, None) == big["workspace_bytes"]
+    t = _capi.tuning(path=_capi.PATH_FUSED, cluster=2, threads=512)
+    assert _capi.plan(8, 1000, 72, t)["cluster"] == 2
+    with pytest.raises(_capi.PhnmsError):
+        _capi.plan(8, 1000, 72, _capi.tuning(cluster=3))
+    with pytest.raises(_capi.PhnmsError):
+        _capi.plan(8, 8192, 72, _capi.tuning(path=_capi.PATH_FUSED, cluster=1))   # does not fit one CTA
+
+
+def test_python_mirror_refuses_cpu_tensors():
+    import torch
+    from phnet_b200.ops import nms
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nms(torch.zeros(8, 77), torch.zeros(8), overlap=50, top_k=4)
+
+
+def test_install_as_libs_ops():
+    import sys
+    import phnet_b200
+    phnet_b200.install_as_libs_ops()
+    from libs.ops import nms as shim  # noqa: E402
+    from phnet_b200.ops import nms
+    assert shim is nms
+    for k in ("libs", "libs.ops", "libs.ops.nms"):
+        sys.modules.pop(k, None)

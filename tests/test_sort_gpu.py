@@ -46,4 +46,4 @@ def test_stable_model_matches_torch_stable(cuda_device):
     g = torch.Generator().manual_seed(9)
     for N in (2, 17, 32, 33, 128, 1000, 5000):
         s = nasty(N, 1, g).to(cuda_device)
-        assert torch.equal(sort_order(s, sort_model=1), torch.sort(s, 0, True, stable=True)[1]), N
+        assert torch.equal(sort_order(s, sort_model=2), torch.sort(s, dim=0, descending=True, stable=True)[1]), N
