@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of lane NMS (1000 proposals x 72 offsets, overlap 50, top_k 4) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference semantics on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU, frames sharded (weak scaling)
+
+One "step" = one pass of the hot path over one batch of synthetic frames (default 16384 frames per GPU = 5.05 GB of
+proposals, far larger than the 126 MB L2, so every step streams from HBM).  Prints ONE JSON line (rank 0).
+
+  value     frames/s, whole job, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
+  e2e       frames/s through the host-buffer API (phnet_b200.ops.HostLaneNMS): pinned host inputs, H2D, kernel, D2H of
+            the reference-shaped results inside the timed region
+  roofline  algorithmic bytes per launch / mean kernel duration (CUDA events around each launch) vs the measured HBM peak
+  cpu_baseline  the CPU oracle (a port of the reference algorithm) on the host cores, bounded sample, rank 0, N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lane_nms_frames_per_sec"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=16384, help="frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=4096, help="frames per GPU per end-to-end step")
+    ap.add_argument("--proposals", type=int, default=1000)
+    ap.add_argument("--offsets", type=int, default=72)
+    ap.add_argument("--top-k", type=int, default=4)
+    ap.add_argument("--overlap", type=float, default=50.0)
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--max-clusters", type=int, default=0)
+    ap.add_argument("--path", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_frame(N: int, n_off: int) -> int:
+    """read proposals + scores once, write keep / parent / count once."""
+    return N * (4 * n_off + 40) + 8
+
+
+def workload_name(a) -> str:
+    return (f"lane NMS, {a.proposals} proposals x {a.offsets} offsets fp32 per frame, overlap {a.overlap:g}, top_k {a.top_k} "
+            f"(BASELINE configs[1] frame shape; batch scaled to {a.frames} frames/GPU/step so inputs exceed L2)")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, torch_index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            self.nv = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML sampling unavailable"}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(N, n_off, frames):
+    """dram bytes per launch from the committed ncu --set full capture, scaled per frame (profiles/roofline_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)
+        key = f"N{N}_No{n_off}"
+        return float(t[key]["dram_bytes_per_frame"]) * frames
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(a, frames, threads, repeat=1):
+    """frames/s of the CPU oracle (literal reference algorithm: full 64x64-tile bitmask + serial collect)."""
+    from oracle import oracle
+    from phnet_b200 import synth
+    props, scores = synth.make_frames(frames, a.proposals, a.offsets, seed=a.seed + 991)
+    p, s = props.numpy(), scores.numpy()
+    best = None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        oracle.nms_batched(p, s, None, a.overlap, a.top_k, lazy=False, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return frames / best, best
+
+
+def run_reference(a):
+    """`--impl reference`: the reference has no CPU implementation of this path (libs/ops is CUDA only, nms.cpp:40), so
+    this arm times the CPU oracle -- the restatement of the reference algorithm pinned against the reference's own
+    kernels -- on every host core.  Each step is a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from phnet_b200 import synth
+    cores = oracle.max_threads()
+    probe_rate, _ = cpu_oracle_rate(a, max(cores, 8), cores)
+    sample = max(cores, int(probe_rate * 1.0))                   # about one second of host work per step
+    props, scores = synth.make_frames(sample, a.proposals, a.offsets, seed=a.seed)
+    p, s = props.numpy(), scores.numpy()
+    for _ in range(a.warmup):
+        oracle.nms_batched(p, s, None, a.overlap, a.top_k, lazy=False, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oracle.nms_batched(p, s, None, a.overlap, a.top_k, lazy=False, threads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * a.steps / dt
+    sample_desc = f"{sample} frames of the same workload per step (CPU-generated, seed {a.seed}), {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "frames_per_step": sample, "proposals": a.proposals,
+                   "offsets": a.offsets, "overlap": a.overlap, "top_k": a.top_k,
+                   "note": "reference libs/ops has no CPU path; this is its algorithm restated in C (oracle/), all host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from phnet_b200 import _capi, sharding, synth
+    from phnet_b200.ops import HostLaneNMS, nms_batched
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the lane-NMS op has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.lib()  # fail loudly before allocating anything if the native library is missing
+
+    N, n_off, F = a.proposals, a.offsets, a.frames
+    tune = _capi.tuning(path=a.path, cluster=a.cluster, threads=a.threads, max_clusters=a.max_clusters)
+    plan = _capi.plan(F, N, n_off, tune)
+
+    # synthetic frames, generated on the device rank by rank (weak scaling: every rank owns `F` frames)
+    props, scores = synth.make_frames_chunked(F, N, n_off, seed=a.seed * 1000 + rank, device=dev)
+    outs = [(torch.empty((F, N), dtype=torch.int64, device=dev), torch.empty((F,), dtype=torch.int64, device=dev),
+             torch.empty((F, N), dtype=torch.int64, device=dev)) for _ in range(2)]
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    comm_done = [None, None]
+    gathered = [None]
+
+    def step(i, ev_pair=None):
+        b = i & 1
+        cur = torch.cuda.current_stream(dev)
+        if comm_done[b] is not None:
+            cur.wait_event(comm_done[b])          # the collect of step i-2 has finished reading this output buffer
+        if ev_pair is not None:
+            ev_pair[0].record(cur)
+        nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b])
+        if ev_pair is not None:
+            ev_pair[1].record(cur)
+        if world > 1:                             # final collection of the kept lanes: one all-gather over NVLink
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                packed = sharding.pack_kept(outs[b][0], outs[b][1], a.top_k)
+                gathered[0] = sharding.gather_kept(packed, F * world)
+                done = torch.cuda.Event()
+                done.record(comm)
+                comm_done[b] = done
+
+    def fence():
+        if comm is not None:
+            torch.cuda.current_stream(dev).wait_stream(comm)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    fence()
+
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for i in range(a.steps):
+            step(i, pairs[i])
+        if comm is not None:
+            torch.cuda.current_stream(dev).wait_stream(comm)
+        e1.record()
+        fence()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = statistics.mean(p0.elapsed_time(p1) for p0, p1 in pairs)
+    if world > 1:
+        t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, kern_ms = float(t[0]), float(t[1])
+    value = world * F * a.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer API ------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        Fe = min(a.e2e_frames, F)
+        pipe = HostLaneNMS(N, n_off, chunk_frames=min(1024, Fe), device=dev)
+        props_h = torch.empty((Fe, N, 5 + n_off), dtype=torch.float32).pin_memory()
+        scores_h = torch.empty((Fe, N), dtype=torch.float32).pin_memory()
+        props_h.copy_(props[:Fe])
+        scores_h.copy_(scores[:Fe])
+        out_h = pipe.alloc_outputs(Fe)
+        for _ in range(3):
+            pipe(props_h, scores_h, a.overlap, a.top_k, out=out_h, tuning=tune)
+        fence()
+        pipe.h2d_bytes = pipe.d2h_bytes = pipe.launches = 0
+        e2e_steps = max(3, min(a.steps, 20))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(e2e_steps):
+            pipe(props_h, scores_h, a.overlap, a.top_k, out=out_h, tuning=tune)
+        s1.record()
+        fence()
+        ms_e2e = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t[0])
+        # the device path and the host path must agree on the same frames
+        assert torch.equal(out_h[0], outs[(a.steps - 1) & 1][0][:Fe].cpu()), "e2e keep differs from device-resident run"
+        e2e = {"value": world * Fe * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": pipe.h2d_bytes // e2e_steps, "d2h_bytes_per_step": pipe.d2h_bytes // e2e_steps,
+               "frames_per_step_per_gpu": Fe, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+               "api": "phnet_b200.ops.HostLaneNMS (pinned host tensors in, reference-shaped keep/num/parent out)"}
+
+    # ---- CPU baseline: the oracle on the host cores, bounded sample ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle
+        cores = oracle.max_threads()
+        probe, _ = cpu_oracle_rate(a, max(cores, 8), cores)
+        sample = max(cores, int(probe * 12.0))     # about 12 s of host work
+        rate, dt = cpu_oracle_rate(a, sample, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample} frames of the same workload in {dt:.1f} s on {cores} threads (oracle/lane_nms_oracle.c, literal N^2 form)"}
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        bpf = algorithmic_bytes_per_frame(N, n_off)
+        achieved = F * bpf / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "frames_per_gpu_per_step": F, "global_frames_per_step": F * world,
+                       "proposals": N, "offsets": n_off, "overlap": a.overlap, "top_k": a.top_k,
+                       "l2": f"inputs are {F * N * (6 + n_off) * 4 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
+                       "parallelism": f"frames sharded x{world}; no data-path collective; kept lanes all-gathered (NCCL) once per step" if world > 1 else "single GPU",
+                       "plan": plan},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(N, n_off, F), "peak_source": peak_src,
+                         "algorithmic_bytes_per_frame": bpf, "kernel": "phnms_fused_kernel" if plan["path"] == 1 else "phnms_mask_kernel",
+                         "kernel_ms_per_launch": kern_ms},
+            "clocks": clocks.summary(),
+            "gpu_launches": a.steps * plan["launches"],
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PHNMS_ABI_VERSION 1
+#define PHNMS_ABI_VERSION 2
 
 #define PHNMS_OK 0
 #define PHNMS_ERR_BAD_ARG (-1)      /* null pointer, negative size, misaligned pointer                         */
@@ -49,11 +49,16 @@ extern "C" {
 #define PHNMS_PATH_FUSED 1          /* one cluster of CTAs per frame, proposals resident in shared memory, lazy rows   */
 #define PHNMS_PATH_TILED 2          /* three kernels: radix order -> 64x64 tile bitmask -> warp-ballot greedy scan     */
 
+/* variants of the fused path */
+#define PHNMS_FUSED_SMEM 1          /* proposals stay in shared memory; any n_off in [1, 250]                          */
+#define PHNMS_FUSED_REG 2           /* proposals held in registers, next frame's TMA load overlaps compute; n_off 36/72 */
+
 typedef struct phnms_tuning {
     int path;            /* PHNMS_PATH_*                                             (0 = auto) */
     int cluster;         /* CTAs per frame for the fused path: 1,2,4,8,16            (0 = auto) */
     int threads;         /* threads per CTA for the fused path: multiple of 32, <=512 (0 = auto) */
     int max_clusters;    /* cap on resident clusters (persistent grid size)          (0 = auto) */
+    int variant;         /* fused path: PHNMS_FUSED_SMEM or PHNMS_FUSED_REG          (0 = auto) */
 } phnms_tuning;
 
 typedef struct phnms_plan {
@@ -64,6 +69,8 @@ typedef struct phnms_plan {
     int smem_bytes;      /* dynamic shared memory per CTA */
     int grid;            /* CTAs launched */
     int launches;        /* kernel launches one phnms_forward_f32 call makes */
+    int variant;         /* PHNMS_FUSED_SMEM / PHNMS_FUSED_REG (fused path), 0 otherwise */
+    int cols_per_thread; /* proposals held per thread (register-resident variant) */
     size_t workspace_bytes;
 } phnms_plan;
 

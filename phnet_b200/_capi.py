@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "csrc", "libphnms.so")
 
 PATH_AUTO, PATH_FUSED, PATH_TILED = 0, 1, 2
+FUSED_SMEM, FUSED_REG = 1, 2
 SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
 
 EXPORTS = (
@@ -18,13 +19,14 @@ EXPORTS = (
 
 class Tuning(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
-                ("max_clusters", ctypes.c_int)]
+                ("max_clusters", ctypes.c_int), ("variant", ctypes.c_int)]
 
 
 class Plan(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
                 ("rows_per_cta", ctypes.c_int), ("smem_bytes", ctypes.c_int), ("grid", ctypes.c_int),
-                ("launches", ctypes.c_int), ("workspace_bytes", ctypes.c_size_t)]
+                ("launches", ctypes.c_int), ("variant", ctypes.c_int), ("cols_per_thread", ctypes.c_int),
+                ("workspace_bytes", ctypes.c_size_t)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -65,7 +67,7 @@ def lib() -> ctypes.CDLL:
     L.phnms_order_workspace_bytes.restype = sz
     L.phnms_order_f32.argtypes = [vp, vp, i64, i64, ci, vp, vp, sz, vp]
     L.phnms_order_f32.restype = ci
-    if L.phnms_abi_version() != 1:
+    if L.phnms_abi_version() != 2:
         raise ImportError("libphnms.so ABI version mismatch; rebuild with `python -m phnet_b200.build`")
     _lib = L
     return L
@@ -76,10 +78,10 @@ def check(code: int) -> None:
         raise PhnmsError(code, lib().phnms_error_string(code).decode())
 
 
-def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0):
-    if not (path or cluster or threads or max_clusters):
+def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0, variant: int = 0):
+    if not (path or cluster or threads or max_clusters or variant):
         return None
-    return Tuning(path, cluster, threads, max_clusters)
+    return Tuning(path, cluster, threads, max_clusters, variant)
 
 
 def plan(F: int, N: int, n_off: int, tune: Tuning | None = None) -> dict:

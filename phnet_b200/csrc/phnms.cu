@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #include "fused_nms.cuh"
+#include "fused_reg.cuh"
 #include "tiled_nms.cuh"
 
 using namespace phnms;
@@ -48,61 +49,112 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
     const int P = 5 + n_off;
     const int smem_max = dev ? dev->smem_optin : 232448;
     const int sms = dev ? dev->sms : 148;
-    phnms_tuning t = {0, 0, 0, 0};
+    phnms_tuning t = {0, 0, 0, 0, 0};
     if (tun) t = *tun;
     pl->workspace_bytes = 0;
     pl->launches = 1;
+    pl->variant = 0;
+    pl->cols_per_thread = 1;
+    const int cand[5] = {1, 2, 4, 8, 16};
 
-    auto fits = [&](int c, FusedLayout *L, int *rpc) {
+    auto rows_for = [&](int c) {
         int r = (int)((N + c - 1) / c);
-        if (r < 32) r = 32;  // a frame of <= 32 proposals lives in one CTA (bitonic replay needs all of them)
-        *rpc = r;
-        *L = fused_layout(r, P, c);
-        return L->total <= smem_max;
+        return r < 32 ? 32 : r;  // a frame of <= 32 proposals lives in one CTA (bitonic replay needs all of them)
     };
 
-    int csize = 0, rpc = 0;
-    FusedLayout L;
     if (t.path != PHNMS_PATH_TILED) {
+        // ---- register-resident variant: n_off 36 / 72 only; a CTA holds at most 512 threads x cols_per_thread rows
+        const bool reg_ok = (n_off == 36 || n_off == 72) && t.variant != PHNMS_FUSED_SMEM;
+        if (reg_ok) {
+            const int max_cpt = (n_off == 36) ? 2 : 1;
+            int csize = 0;
+            for (int i = 0; i < 5 && !csize; ++i) {
+                const int c = cand[i];
+                if (t.cluster && c != t.cluster) continue;
+                const int rpc = rows_for(c);
+                if (rpc > 512 * max_cpt) continue;
+                if (freg_layout(rpc, P, c).total > smem_max) continue;
+                csize = c;
+            }
+            if (csize) {
+                const int rpc = rows_for(csize);
+                int threads = t.threads ? t.threads : round_up(rpc, 32);
+                if (threads > 512) threads = 512;
+                if (threads < 128) threads = 128;
+                if (threads % 32) return PHNMS_ERR_TUNING;
+                int cpt = (rpc + threads - 1) / threads;
+                if (cpt > max_cpt) {
+                    if (t.threads) return PHNMS_ERR_TUNING;
+                    threads = 512;
+                    cpt = (rpc + threads - 1) / threads;
+                }
+                const FregLayout L = freg_layout(rpc, P, csize);
+                int per_sm = smem_max / (L.total + 1024);
+                const int by_regs = 65536 / (threads * 128);   // __launch_bounds__(512, 1): up to 128 registers per thread
+                if (per_sm > by_regs) per_sm = by_regs;
+                if (per_sm < 1) per_sm = 1;
+                long long resident = (long long)(sms / csize) * per_sm;
+                if (resident < 1) resident = 1;
+                if (t.max_clusters > 0 && resident > t.max_clusters) resident = t.max_clusters;
+                long long clusters = F < resident ? F : resident;
+                if (clusters < 1) clusters = 1;
+                pl->path = PHNMS_PATH_FUSED;
+                pl->variant = PHNMS_FUSED_REG;
+                pl->cluster = csize;
+                pl->threads = threads;
+                pl->cols_per_thread = cpt;
+                pl->rows_per_cta = rpc;
+                pl->smem_bytes = L.total;
+                pl->grid = (int)(clusters * csize);
+                return PHNMS_OK;
+            }
+            if (t.variant == PHNMS_FUSED_REG) return PHNMS_ERR_TUNING;
+        } else if (t.variant == PHNMS_FUSED_REG) {
+            return PHNMS_ERR_TUNING;
+        }
+
+        // ---- shared-memory-resident variant: any n_off
+        int csize = 0, rpc = 0;
+        FusedLayout L;
+        auto fits = [&](int c) {
+            rpc = rows_for(c);
+            L = fused_layout(rpc, P, c);
+            return L.total <= smem_max;
+        };
         if (t.cluster) {
             const int c = t.cluster;
             if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 16)) return PHNMS_ERR_TUNING;
-            if (!fits(c, &L, &rpc)) return PHNMS_ERR_TUNING;
+            if (!fits(c)) return PHNMS_ERR_TUNING;
             csize = c;
         } else {
-            // smallest cluster that leaves room for two CTAs per SM (load of one frame overlaps compute of another),
-            // else the smallest that fits at all
-            const int cand[5] = {1, 2, 4, 8, 16};
-            for (int i = 0; i < 4 && !csize; ++i)
-                if (fits(cand[i], &L, &rpc) && L.total <= smem_max / 2 - 1024) csize = cand[i];
             for (int i = 0; i < 5 && !csize; ++i)
-                if (fits(cand[i], &L, &rpc)) csize = cand[i];
+                if (fits(cand[i])) csize = cand[i];
         }
-        if (!csize && t.path == PHNMS_PATH_FUSED) return PHNMS_ERR_TUNING;
-    }
-
-    if (csize) {
-        fits(csize, &L, &rpc);
-        int threads = t.threads ? t.threads : round_up(rpc, 32);
-        if (threads > 512) threads = 512;
-        if (threads < 128) threads = 128;
-        if (threads % 32) return PHNMS_ERR_TUNING;
-        int per_sm = smem_max / (L.total + 1024);
-        if (per_sm > 2048 / threads) per_sm = 2048 / threads;
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 32) per_sm = 32;
-        long long resident = (long long)(sms / csize) * per_sm;
-        if (resident < 1) resident = 1;
-        if (t.max_clusters > 0 && resident > t.max_clusters) resident = t.max_clusters;
-        long long clusters = F < resident ? F : resident;
-        if (clusters < 1) clusters = 1;
-        pl->path = PHNMS_PATH_FUSED;
-        pl->cluster = csize;
-        pl->threads = threads;
-        pl->rows_per_cta = rpc;
-        pl->smem_bytes = L.total;
-        pl->grid = (int)(clusters * csize);
-        return PHNMS_OK;
+        if (csize) {
+            fits(csize);
+            int threads = t.threads ? t.threads : round_up(rpc, 32);
+            if (threads > 512) threads = 512;
+            if (threads < 128) threads = 128;
+            if (threads % 32) return PHNMS_ERR_TUNING;
+            int per_sm = smem_max / (L.total + 1024);
+            if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 32) per_sm = 32;
+            long long resident = (long long)(sms / csize) * per_sm;
+            if (resident < 1) resident = 1;
+            if (t.max_clusters > 0 && resident > t.max_clusters) resident = t.max_clusters;
+            long long clusters = F < resident ? F : resident;
+            if (clusters < 1) clusters = 1;
+            pl->path = PHNMS_PATH_FUSED;
+            pl->variant = PHNMS_FUSED_SMEM;
+            pl->cluster = csize;
+            pl->threads = threads;
+            pl->rows_per_cta = rpc;
+            pl->smem_bytes = L.total;
+            pl->grid = (int)(clusters * csize);
+            return PHNMS_OK;
+        }
+        if (t.path == PHNMS_PATH_FUSED) return PHNMS_ERR_TUNING;
     }
 
     pl->path = PHNMS_PATH_TILED;
@@ -117,11 +169,12 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
     return PHNMS_OK;
 }
 
-int launch_fused(const phnms_plan &pl, const FusedParams &fp, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(phnms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+template <typename Kern, typename... Args>
+int launch_cluster(Kern kern, const phnms_plan &pl, cudaStream_t stream, Args... args) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return (int)e;
     if (pl.cluster > 8) {
-        e = cudaFuncSetAttribute(phnms_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return (int)e;
     }
     cudaLaunchConfig_t cfg = {};
@@ -136,8 +189,7 @@ int launch_fused(const phnms_plan &pl, const FusedParams &fp, cudaStream_t strea
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, phnms_fused_kernel, fp);
-    return (int)e;
+    return (int)cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 }  // namespace
@@ -234,7 +286,13 @@ int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_
         fp.sort_model = sort_model;
         fp.thr = thresh;
         fp.L = fused_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
-        return launch_fused(pl, fp, stream);
+        if (pl.variant == PHNMS_FUSED_REG) {
+            const FregLayout RL = freg_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
+            if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1>, pl, stream, fp, RL);
+            if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1>, pl, stream, fp, RL);
+            return launch_cluster(phnms_freg_kernel<36, 2>, pl, stream, fp, RL);
+        }
+        return launch_cluster(phnms_fused_kernel, pl, stream, fp);
     }
 
     // ---- tiled path: order -> bitmask -> scan ------------------------------------------------------------

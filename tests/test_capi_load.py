@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == set(_capi.EXPORTS), "include/phnms.h and the ctypes binding disagree"
     for s in syms:
         assert hasattr(L, s), f"libphnms.so does not export {s}"
-    assert L.phnms_abi_version() == 1
+    assert L.phnms_abi_version() == 2
 
 
 def test_library_is_sm100a_only_and_has_tma_and_cluster_code():

@@ -27,12 +27,42 @@ def test_fused_auto_shapes(cuda_device, N, n_off):
         run_both(props, scores, 50.0, top_k, cuda_device, ctx=f"N={N} No={n_off} top_k={top_k}")
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("cluster,threads", [(1, 128), (1, 512), (2, 256), (2, 512), (4, 128), (4, 256), (8, 128), (16, 128)])
-def test_fused_cluster_sizes(cuda_device, cluster, threads):
-    props, scores = synth.make_frames(9, 700, 72, seed=cluster * 100 + threads)
-    for top_k in (1, 4, 0):
-        run_both(props, scores, 50.0, top_k, cuda_device, tuning=dict(path=1, cluster=cluster, threads=threads),
-                 ctx=f"cluster={cluster} threads={threads} top_k={top_k}")
+def test_fused_cluster_sizes(cuda_device, cluster, threads, variant):
+    from phnet_b200 import _capi
+    for n_off, N in ((72, 700), (36, 900), (72, 240), (36, 1000)):
+        tuning = dict(path=1, cluster=cluster, threads=threads, variant=variant)
+        try:
+            plan(9, N, n_off, tuning)
+        except _capi.PhnmsError:
+            continue   # this combination does not fit (e.g. 700 rows x 72 offsets in one CTA's registers)
+        props, scores = synth.make_frames(9, N, n_off, seed=cluster * 100 + threads + N)
+        for top_k in (1, 4, 0):
+            run_both(props, scores, 50.0, top_k, cuda_device, tuning=tuning,
+                     ctx=f"variant={variant} cluster={cluster} threads={threads} N={N} No={n_off} top_k={top_k}")
+
+
+def test_both_fused_variants_on_edge_and_ragged(cuda_device):
+    F, N = 24, 300
+    g = torch.Generator().manual_seed(4)
+    for n_off in (72, 36):
+        props, scores = synth.make_frames(F, N, n_off, seed=6, ties=True)
+        n_valid = torch.randint(0, N + 1, (F,), generator=g, dtype=torch.int32)
+        n_valid[0], n_valid[1], n_valid[2], n_valid[3], n_valid[4] = 0, 1, N, 32, 20
+        for variant in (1, 2):
+            for cluster in (1, 2, 4):
+                run_both(props, scores, 50.0, 4, cuda_device, n_valid=n_valid,
+                         tuning=dict(path=1, cluster=cluster, variant=variant),
+                         ctx=f"ragged variant={variant} cluster={cluster} No={n_off}")
+        for seed in range(6):
+            p, s = synth.edge_frame(n_off, seed=seed)
+            for variant in (1, 2):
+                for cluster in (1, 2):
+                    for top_k in (0, 4):
+                        run_both(p[None], s[None], 50.0, top_k, cuda_device,
+                                 tuning=dict(path=1, cluster=cluster, variant=variant),
+                                 ctx=f"edge variant={variant} cluster={cluster} No={n_off} seed={seed} top_k={top_k}")
 
 
 @pytest.mark.parametrize("top_k", [0, 1, 2, 4, 8, 1000, 5000])
@@ -55,7 +85,7 @@ def test_edge_frames(cuda_device, n_off):
         p, s = synth.edge_frame(n_off, seed=seed)
         for top_k in (0, 1, 4, 8, 96):
             for thr in (50.0, 0.0, -1.0, float("nan"), float("inf")):
-                for tuning in (None, dict(path=1, cluster=2, threads=128), dict(path=2)):
+                for tuning in (None, dict(path=1, cluster=2, threads=128), dict(path=1, variant=1), dict(path=2)):
                     run_both(p[None], s[None], thr, top_k, cuda_device, tuning=tuning,
                              ctx=f"edge seed={seed} No={n_off} top_k={top_k} thr={thr} tuning={tuning}")
 
@@ -70,7 +100,7 @@ def test_score_ties_all_sort_models(cuda_device):
             scores[2, ::2] = 0.0
             scores[2, 1::4] = -0.0
         for sm in (0, 1, 2):
-            for tuning in (None, dict(path=2)):
+            for tuning in (None, dict(path=1, variant=1), dict(path=2)):
                 run_both(props, scores, 50.0, 4, cuda_device, sort_model=sm, tuning=tuning,
                          ctx=f"ties N={N} sort_model={sm} tuning={tuning}")
 
@@ -170,9 +200,10 @@ def test_full_size_properties(cuda_device):
     k3, n3, _ = nms_batched(sub, subs, 50.0, 4, num.to(torch.int32))
     assert torch.equal(n3, num)
     assert ((k3[:, :4] == torch.arange(4, device=cuda_device)[None, :]) | ~valid).all()
-    # (5) fused and tiled paths agree on a 32-frame clip (config 2)
-    kt, nt, pt = nms_batched(props[:32], scores[:32], 50.0, 4, tuning=dict(path=2))
-    assert torch.equal(kt, keep[:32]) and torch.equal(nt, num[:32]) and torch.equal(pt, parent[:32])
+    # (5) all three device algorithms agree on a 32-frame clip (config 2)
+    for tuning in (dict(path=2), dict(path=1, variant=1), dict(path=1, variant=2, cluster=4)):
+        kt, nt, pt = nms_batched(props[:32], scores[:32], 50.0, 4, tuning=tuning)
+        assert torch.equal(kt, keep[:32]) and torch.equal(nt, num[:32]) and torch.equal(pt, parent[:32]), tuning
 
 
 def test_error_behaviour(cuda_device):
