@@ -71,6 +71,7 @@ typedef struct phnms_plan {
     int launches;        /* kernel launches one phnms_forward_f32 call makes */
     int variant;         /* PHNMS_FUSED_SMEM / PHNMS_FUSED_REG (fused path), 0 otherwise */
     int cols_per_thread; /* proposals held per thread (register-resident variant) */
+    int max_active_clusters; /* cudaOccupancyMaxActiveClusters for this launch (0 when no device was queried) */
     size_t workspace_bytes;
 } phnms_plan;
 
@@ -101,6 +102,13 @@ int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_
                       int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
                       int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning /* nullable */,
                       void *stream);
+
+/* Same call with a profiling hook: when `trace` (device, int64[trace_len]) is not NULL, thread 0 of CTA 0 of the
+ * register-resident fused kernel appends (phase tag, clock64()) pairs at its phase boundaries. */
+int phnms_forward_f32_trace(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
+                            int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
+                            int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream,
+                            int64_t *trace, int trace_len);
 
 /*
  * The ordering alone (libs/ops/csrc/nms.cpp:51): order[f, i] = original index of the i-th proposal of frame f

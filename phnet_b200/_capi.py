@@ -13,7 +13,7 @@ SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
 
 EXPORTS = (
     "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query",
-    "phnms_forward_f32", "phnms_order_workspace_bytes", "phnms_order_f32",
+    "phnms_forward_f32", "phnms_forward_f32_trace", "phnms_order_workspace_bytes", "phnms_order_f32",
 )
 
 
@@ -25,7 +25,7 @@ class Tuning(ctypes.Structure):
 class Plan(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
                 ("rows_per_cta", ctypes.c_int), ("smem_bytes", ctypes.c_int), ("grid", ctypes.c_int),
-                ("launches", ctypes.c_int), ("variant", ctypes.c_int), ("cols_per_thread", ctypes.c_int),
+                ("launches", ctypes.c_int), ("variant", ctypes.c_int), ("cols_per_thread", ctypes.c_int), ("max_active_clusters", ctypes.c_int),
                 ("workspace_bytes", ctypes.c_size_t)]
 
     def as_dict(self):
@@ -63,6 +63,8 @@ def lib() -> ctypes.CDLL:
     L.phnms_forward_f32.argtypes = [vp, vp, vp, i64, i64, ci, ctypes.c_float, i64, ci, vp, vp, vp, vp, sz,
                                     ctypes.POINTER(Tuning), vp]
     L.phnms_forward_f32.restype = ci
+    L.phnms_forward_f32_trace.argtypes = L.phnms_forward_f32.argtypes + [vp, ci]
+    L.phnms_forward_f32_trace.restype = ci
     L.phnms_order_workspace_bytes.argtypes = [i64, i64]
     L.phnms_order_workspace_bytes.restype = sz
     L.phnms_order_f32.argtypes = [vp, vp, i64, i64, ci, vp, vp, sz, vp]

@@ -144,6 +144,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Debug variant: gives up after ~2^22 polls and appends {tag, block, thread, parity, a, b} to `dbg` (first word = count).
+__device__ __forceinline__ bool mbar_wait_watch(uint32_t bar, uint32_t parity, long long *dbg, int tag, long long a,
+                                                long long b) {
+    for (unsigned it = 0; it < (1u << 22); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long *>(dbg), 1ull);
+    if (slot < 200) {
+        long long *r = dbg + 8 + slot * 8;
+        r[0] = tag; r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = parity; r[4] = a; r[5] = b;
+    }
+    return false;
+}
 // TMA 1-D bulk copy global -> shared (UBLKCP); completes `bytes` on the mbarrier.
 // src and dst 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {

@@ -48,6 +48,9 @@ struct FusedParams {
     int sort_model;
     float thr;
     FusedLayout L;
+    const int *topm;   // optional [F, kTopM] candidate slots (header + row) of the best-ranked proposals (phnms_topm_kernel)
+    long long *trace;  // optional: CTA 0 / thread 0 writes clock64() at phase boundaries (phnms_forward_f32_trace)
+    int trace_len;
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -144,7 +147,6 @@ __global__ void __launch_bounds__(512, 1) phnms_fused_kernel(const FusedParams p
         if (bulk) {
             if (tid == 0) {
                 const uint32_t total = (uint32_t)(e_al - s_al);
-                fence_proxy_async();
                 mbar_arrive_expect_tx(bar, total);
                 uint32_t chunk = ((total / 8 + 15) & ~15u);
                 if (chunk < 4096u) chunk = 4096u;

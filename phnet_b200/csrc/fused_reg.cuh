@@ -21,11 +21,23 @@
 
 namespace phnms {
 
+constexpr int kCand = 4;   // candidates every CTA publishes per exchange (fallback batches)
+constexpr int kTopM = 8;   // per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch)
+constexpr int kHdr = 32;   // candidate header bytes: {key, index, start, end, mask0, mask1, mask2, aux}
+
+// A candidate slot = 32-byte header + the proposal's row padded to a multiple of 4 words.
+//   key/index : rank key (key << 32 | index orders the frame), original proposal index
+//   start/end : the lane's own bounds (nms_kernel.cu:29-34), end clamped to n_off-1
+//   mask0..2  : the lane's in-range bitmask over row words (range_mask)
+//   aux       : precomputed records: number of valid candidates of the frame (record 0);
+//               compacted fallback headers: index of the slot that holds the row
 struct FregLayout {
-    int off_wred;     // 2 x 32 x u64 (double buffered per round parity)
+    int off_wtop;     // 2 parities x 32 warps x kCand x u64: per-warp best alive keys
+    int off_bh;       // 32 x 32 B compacted headers of a fallback batch, in rank order; then count; then 3 x 32 dead flags
     int off_bit;      // bitonic scratch
-    int off_slots;    // 2 parities x csize slots
-    int slot_stride;  // 16 + 4 * round4(P)
+    int off_slots;    // 2 parities x csize x kCand exchange slots
+    int slot_stride;  // kHdr + 4 * round4(P)
+    int off_pslots;   // 2 frame parities x kTopM slots: precomputed candidates of the current / next frame
     int off_rows;     // staging: 16 B lead + rpc*P*4 + pad
     int total;
 };
@@ -33,14 +45,18 @@ struct FregLayout {
 inline FregLayout freg_layout(int rpc, int P, int csize) {
     FregLayout L;
     int o = 32;  // mbarriers: load @0, exchange @8 and @16
-    L.off_wred = o;
-    o += 2 * 32 * 8;
+    L.off_wtop = o;
+    o += 2 * 32 * kCand * 8;
+    L.off_bh = o;
+    o += 32 * kHdr + 16 + 3 * 32 * 4;
     L.off_bit = o;
     o += 32 * 12;
     o = round_up(o, 16);
     L.off_slots = o;
-    L.slot_stride = 16 + 4 * round_up(P, 4);
-    o += 2 * csize * L.slot_stride;
+    L.slot_stride = kHdr + 4 * round_up(P, 4);
+    o += 2 * csize * kCand * L.slot_stride;
+    L.off_pslots = o;
+    o += 2 * kTopM * L.slot_stride;
     L.off_rows = o;
     o += 16 + round_up(rpc * P * 4, 16) + 32;
     L.total = o;
@@ -61,6 +77,19 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 
+// Bits [5+start, 5+end] of one lane's own offset range (start below -5 acts as "no lower bound": the other lane's
+// start wins the max).  Bit i corresponds to row word i (columns 0..4 are the header, nms_kernel.cu:38).
+template <int MW>
+__device__ __forceinline__ void range_mask(int start, int end, uint32_t (&m)[MW]) {
+    const int lo = start < -5 ? 0 : min(start, 1 << 20) + 5;   // (clamps keep the int arithmetic below from wrapping)
+    const int hi = max(end, -(1 << 20)) + 5;                   // end is already clamped to NOFF-1 from above
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        const int l = max(lo - 32 * w, 0), h = min(hi - 32 * w, 31);
+        m[w] = (l <= h) ? ((0xffffffffu >> (31 - h)) & (0xffffffffu << l)) : 0u;
+    }
+}
+
 struct Slab {       // what one CTA loads for one frame
     int nv;         // real proposals in the frame
     int r0;         // first row owned by this CTA
@@ -71,8 +100,11 @@ struct Slab {       // what one CTA loads for one frame
 
 // Requests frame f's slab: TMA bulk copy of the 16-byte aligned body (completes on `bar`), the <= 3 unaligned words at
 // either end by ordinary loads.  Call with the staging buffer free (after a __syncthreads that follows its last read).
+// When phnms_topm_kernel ran, the frame's candidate block (kTopM slots, laid out exactly like pslots) rides along as
+// one more bulk copy on the same mbarrier.
 __device__ __forceinline__ Slab request_slab(const FusedParams &p, long long f, uint32_t rank, unsigned char *rows_buf,
-                                             uint32_t bar, int tid, int T, int P) {
+                                             uint32_t bar, int tid, int T, int P, unsigned char *cand_dst,
+                                             uint32_t cand_bytes) {
     Slab s;
     s.nv = p.N;
     if (p.n_valid) s.nv = max(0, min(p.n_valid[f], p.N));
@@ -81,19 +113,36 @@ __device__ __forceinline__ Slab request_slab(const FusedParams &p, long long f, 
     const float *src = p.props + ((size_t)f * p.N + s.r0) * P;
     const uintptr_t b = (uintptr_t)src, e = b + (size_t)s.nloc * P * 4;
     const uintptr_t b_al = (b + 15) & ~(uintptr_t)15, e_al = e & ~(uintptr_t)15;
-    s.bulk = e_al > b_al;
-    s.head = s.bulk ? (int)(b_al - b) : 0;
+    const bool body = e_al > b_al;
+    const bool cand = p.topm != nullptr;
+    s.bulk = body || cand;
+    s.head = body ? (int)(b_al - b) : 0;
     float *rows = reinterpret_cast<float *>(rows_buf + 16 - s.head);
-    if (s.bulk) {
-        if (tid == 0) {
-            const uint32_t total = (uint32_t)(e_al - b_al);
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar, total);
-            uint32_t chunk = ((total / 8 + 15) & ~15u);
-            if (chunk < 4096u) chunk = 4096u;
-            const uint32_t dst = smem_u32(rows_buf + 16);
-            for (uint32_t off = 0; off < total; off += chunk)
-                bulk_g2s(dst + off, reinterpret_cast<const void *>(b_al + off), min(chunk, total - off), bar);
+    if (cand) {
+        const uint32_t slab_bytes = body ? (uint32_t)(e_al - b_al) : 0u;
+        if (tid == 0) mbar_arrive_expect_tx(bar, slab_bytes + cand_bytes);
+        if (tid == 32)
+            bulk_g2s(smem_u32(cand_dst), reinterpret_cast<const unsigned char *>(p.topm) + (size_t)f * cand_bytes, cand_bytes, bar);
+    }
+    if (body) {
+        // No proxy fence: the generic-proxy READS of the staging buffer are ordered before this async-proxy write by
+        // the __syncthreads that precedes the call (a fence here compiles to MEMBAR and waits for the previous frame's
+        // streaming stores to HBM: 2.3k cycles per frame in the phase trace).  The copy is cut into up to 8 chunks,
+        // each issued by lane 0 of a different warp (back-to-back UBLKCPs from one thread serialise on the TMA queue
+        // and sat on the critical path); a chunk may complete before thread 0 has armed the barrier, which is fine.
+        const uint32_t total = (uint32_t)(e_al - b_al);
+        if (tid == 0 && !cand) mbar_arrive_expect_tx(bar, total);
+        {
+            const int nw = T >> 5, issuers = nw < 8 ? nw : 8;
+            uint32_t chunk = ((total / issuers + 15) & ~15u);
+            if (chunk < 2048u) chunk = 2048u;
+            const int w = (tid >> 5), k = nw - 1 - w;   // last warps issue: warp 0 has the first-batch work ahead of it
+            if ((tid & 31) == 0 && k < issuers) {
+                const uint32_t off = (uint32_t)k * chunk;
+                if (off < total)
+                    bulk_g2s(smem_u32(rows_buf + 16) + off, reinterpret_cast<const void *>(b_al + off),
+                             min(chunk, total - off), bar);
+            }
         }
         const int tail0 = (int)((e_al - b) >> 2), ntail = (int)((e - e_al) >> 2);
         if (tid >= 32 && tid - 32 < (s.head >> 2)) rows[tid - 32] = src[tid - 32];
@@ -104,12 +153,21 @@ __device__ __forceinline__ Slab request_slab(const FusedParams &p, long long f, 
     return s;
 }
 
+#define PHNMS_TRACE(tag)                                                                      \
+    do {                                                                                      \
+        if (p.trace && p.trace_len > 0 && blockIdx.x == 0 && tid == 0 && tcount + 1 < p.trace_len) { \
+            p.trace[tcount++] = (long long)(tag);                                             \
+            p.trace[tcount++] = clock64();                                                    \
+        }                                                                                     \
+    } while (0)
+
 template <int NOFF, int CPT>
 __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p, const FregLayout L) {
     constexpr int P = 5 + NOFF;
-    constexpr int MW = (P + 31) / 32;   // in-range bitmask words
+    constexpr int MW = (P + 31) / 32;   // in-range bitmask words (<= 3)
     constexpr int P4 = (P + 3) & ~3;
-    constexpr int SLOT = 16 + 4 * P4;   // bytes: {key, index, start, end} + padded row
+    constexpr int SLOT = kHdr + 4 * P4;
+    constexpr int M = kCand;
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
@@ -117,11 +175,15 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
     const uint32_t rank = csize > 1 ? cluster_ctarank() : 0u;
     const long long cl = blockIdx.x / csize, ncl = gridDim.x / csize;
 
-    u64 *wred = reinterpret_cast<u64 *>(smem + L.off_wred);
+    u64 *wtop = reinterpret_cast<u64 *>(smem + L.off_wtop);
+    unsigned char *bh = smem + L.off_bh;                                               // [32][kHdr]
+    uint32_t *lcount_p = reinterpret_cast<uint32_t *>(smem + L.off_bh + 32 * kHdr);    // [1]
+    uint32_t *cdead = lcount_p + 4;                                                    // [3][32]
     float *bit_key = reinterpret_cast<float *>(smem + L.off_bit);
     int *bit_val = reinterpret_cast<int *>(smem + L.off_bit + 128);
     int *bit_ok = reinterpret_cast<int *>(smem + L.off_bit + 256);
     unsigned char *slots = smem + L.off_slots;
+    unsigned char *pslots = smem + L.off_pslots;
     unsigned char *rows_buf = smem + L.off_rows;
     const uint32_t bar_load = smem_u32(smem), bar_x0 = bar_load + 8;
 
@@ -137,42 +199,52 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         cluster_wait_acquire();
     }
 
-    uint32_t load_phase = 0, round_ctr = 0;
+    uint32_t load_phase = 0, round_ctr = 0, fpar = 0;
+    int tcount = 0;
     float sc[CPT];       // this frame's scores of my columns
     Slab cur;
     if (cl < p.F) {
-        cur = request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P);
+        cur = request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(kTopM * SLOT));
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int col = c * T + tid;
             sc[c] = col < cur.nloc ? p.scores[(size_t)cl * p.N + cur.r0 + col] : 0.0f;
         }
     }
+    // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
+    // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
+    const int lcap = min(T * CPT - p.rpc, 31);
 
     for (long long f = cl; f < p.F; f += ncl) {
+        PHNMS_TRACE(1);  // frame start
+        if (warp == 0) cdead[2 * 32 + lane] = 0u;            // dead flags of the first batch
         // ---- staging -> registers -------------------------------------------------------------------------------
         if (cur.bulk) {
-            mbar_wait(bar_load, load_phase);
+            if (p.trace_len < 0) mbar_wait_watch(bar_load, load_phase, p.trace, 1, f, round_ctr);
+            else mbar_wait(bar_load, load_phase);
             load_phase ^= 1u;
         }
         __syncthreads();
+        PHNMS_TRACE(2);  // slab landed
         const float *rows = reinterpret_cast<const float *>(rows_buf + 16 - cur.head);
         const int nv = cur.nv, r0 = cur.r0, nloc = cur.nloc;
-        float x[CPT][P];
-        bool valid[CPT];
-        uint32_t key[CPT], par[CPT];
+        float x[CPT][NOFF];   // the offsets only; the 5 header words are re-read on the rare paths that need them
+        bool real[CPT], virt[CPT];
+        uint32_t key[CPT], par[CPT], mb[CPT][MW];
         int st[CPT], en[CPT];
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int col = c * T + tid;
-            valid[c] = col < nloc;
-            const float *row = rows + (size_t)(valid[c] ? col : 0) * P;
+            real[c] = col < nloc;
+            virt[c] = false;
+            const float *row = rows + (size_t)(real[c] ? col : 0) * P;
 #pragma unroll
-            for (int i = 0; i < P; ++i) x[c][i] = row[i];
-            st[c] = lane_start(x[c][2], NOFF);           // nms_kernel.cu:29-30
-            en[c] = lane_end(x[c][4], st[c], NOFF);      // :32-34
+            for (int i = 0; i < NOFF; ++i) x[c][i] = row[5 + i];
+            st[c] = lane_start(row[2], NOFF);            // nms_kernel.cu:29-30
+            en[c] = lane_end(row[4], st[c], NOFF);       // :32-34
             key[c] = key_desc(sc[c], p.sort_model == 1);
             par[c] = 0u;
+            range_mask<MW>(st[c], en[c], mb[c]);
         }
         const bool bitonic = (p.sort_model == 0) && nv <= 32 && nv >= 2;  // torch: unstable bitonic network (n <= 32)
         if (bitonic && warp == 0 && nloc > 0) {  // rank 0 holds the whole frame (rows_per_cta >= 32), column == lane
@@ -198,154 +270,343 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
                     __syncwarp();
                 }
             }
-            // sorted position -> rank key of the proposal that landed there
-            int mypos = 0;
+            int mypos = 0;  // sorted position -> rank key of the proposal that landed there
             for (int q = 0; q < 32; ++q)
                 if (bit_val[q] == lane && q < nv) mypos = q;
             key[0] = (uint32_t)mypos;
         }
         __syncthreads();  // every row is in registers: the staging buffer is free
+        PHNMS_TRACE(3);  // rows in registers
 
         // ---- request the next frame now; it lands while this frame's rounds run ----------------------------------
         Slab nxt;
         nxt.bulk = false; nxt.nv = nxt.r0 = nxt.nloc = nxt.head = 0;
         const long long fn = f + ncl;
         if (fn < p.F) {
-            nxt = request_slab(p, fn, rank, rows_buf, bar_load, tid, T, P);
+            nxt = request_slab(p, fn, rank, rows_buf, bar_load, tid, T, P,
+                               pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(kTopM * SLOT));
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
                 const int col = c * T + tid;
                 sc[c] = col < nxt.nloc ? p.scores[(size_t)fn * p.N + nxt.r0 + col] : 0.0f;
             }
         }
+        PHNMS_TRACE(4);  // next slab requested
 
         u64 myK[CPT];
 #pragma unroll
         for (int c = 0; c < CPT; ++c)
-            myK[c] = valid[c] ? (((u64)key[c] << 32) | (uint32_t)(r0 + c * T + tid)) : kNone64;
+            myK[c] = real[c] ? (((u64)key[c] << 32) | (uint32_t)(r0 + c * T + tid)) : kNone64;
 
-        // ---- greedy rounds: one per kept lane (nms_collect, :111-136) -------------------------------------------
+        // ---- greedy rounds (nms_collect, :111-136), in batches.  Batch 0 uses the frame's kTopM best-ranked proposals
+        // found by phnms_topm_kernel (every CTA fetched the records and rows itself: no selection, no exchange).  If
+        // more lanes are needed, fallback batches follow: every CTA publishes its best kCand alive lanes; the merged
+        // list is exact up to the smallest "last published key" (an unpublished alive lane of CTA d ranks after d's
+        // last published one) and that guaranteed prefix is consumed with no further communication.
         long long n = 0;
-        while (true) {
-            const uint32_t par_bit = round_ctr & 1u, xphase = (round_ctr >> 1) & 1u;
-            ++round_ctr;
-            u64 best = kNone64;
+        bool frame_done = false;
+        bool first_batch = p.topm != nullptr;
+        while (!frame_done) {
+            const unsigned char *hb;   // headers of this batch in rank order
+            int hs;                    // header stride
+            const unsigned char *sl;   // slots that hold the rows
+            uint32_t dead_row;
+            int lcount;
+            const bool fb = first_batch;
+            if (first_batch) {
+                first_batch = false;
+                sl = pslots + (size_t)fpar * kTopM * L.slot_stride;
+                hb = sl;
+                hs = L.slot_stride;
+                dead_row = 2u;
+                lcount = min((int)reinterpret_cast<const uint32_t *>(sl)[7], 1 + lcap);
+            } else {
+                const uint32_t par_bit = round_ctr & 1u, xphase = (round_ctr >> 1) & 1u;
+                ++round_ctr;
+                dead_row = par_bit;
+                // 1. warp-local best M alive lanes
+                u64 wbest[M];
+                bool taken[CPT];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c)
-                if (par[c] == 0u) best = min(best, myK[c]);
-            best = warp_min_u64(best);
-            if (lane == 0) wred[par_bit * 32 + warp] = best;
-            __syncthreads();
-            best = warp_min_u64(lane < nwarps ? wred[par_bit * 32 + lane] : kNone64);
-
-            // publish the CTA's candidate {key, index, start, end, row} into slot[par][rank] of every CTA
-            const uint32_t myslot = smem_u32(slots + (size_t)(par_bit * csize + rank) * L.slot_stride);
-            const uint32_t bar_x = bar_x0 + 8u * par_bit;
-            if (csize > 1 && tid == 0) mbar_arrive_expect_tx(bar_x, (uint32_t)(csize * SLOT));
-            bool owner = false;
+                for (int c = 0; c < CPT; ++c) taken[c] = false;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                if (myK[c] == best && best != kNone64) {
-                    owner = true;
-                    if (csize == 1) {
-                        sts_v4(myslot, (uint32_t)(best >> 32), (uint32_t)best, (uint32_t)st[c], (uint32_t)en[c]);
+                for (int i = 0; i < M; ++i) {
+                    u64 cand = kNone64;
 #pragma unroll
-                        for (int g = 0; g < P4 / 4; ++g)
-                            sts_v4(myslot + 16 + 16 * g, __float_as_uint(x[c][4 * g]),
-                                   4 * g + 1 < P ? __float_as_uint(x[c][4 * g + 1 < P ? 4 * g + 1 : 0]) : 0u,
-                                   4 * g + 2 < P ? __float_as_uint(x[c][4 * g + 2 < P ? 4 * g + 2 : 0]) : 0u,
-                                   4 * g + 3 < P ? __float_as_uint(x[c][4 * g + 3 < P ? 4 * g + 3 : 0]) : 0u);
-                    } else {
-                        for (int d = 0; d < csize; ++d) {
-                            const uint32_t dst = mapa_u32(myslot, (uint32_t)d), dbar = mapa_u32(bar_x, (uint32_t)d);
-                            st_async_v4(dst, (uint32_t)(best >> 32), (uint32_t)best, (uint32_t)st[c], (uint32_t)en[c], dbar);
+                    for (int c = 0; c < CPT; ++c)
+                        if (real[c] && par[c] == 0u && !taken[c]) cand = min(cand, myK[c]);
+                    const u64 b = warp_min_u64(cand);
 #pragma unroll
-                            for (int g = 0; g < P4 / 4; ++g)
-                                st_async_v4(dst + 16 + 16 * g, __float_as_uint(x[c][4 * g]),
-                                            4 * g + 1 < P ? __float_as_uint(x[c][4 * g + 1 < P ? 4 * g + 1 : 0]) : 0u,
-                                            4 * g + 2 < P ? __float_as_uint(x[c][4 * g + 2 < P ? 4 * g + 2 : 0]) : 0u,
-                                            4 * g + 3 < P ? __float_as_uint(x[c][4 * g + 3 < P ? 4 * g + 3 : 0]) : 0u, dbar);
+                    for (int c = 0; c < CPT; ++c)
+                        if (b != kNone64 && myK[c] == b) taken[c] = true;
+                    wbest[i] = b;
+                }
+                {
+                    u64 v = wbest[0];
+#pragma unroll
+                    for (int i = 1; i < M; ++i)
+                        if (lane == i) v = wbest[i];
+                    if (lane < M) wtop[(par_bit * 32 + warp) * M + lane] = v;
+                }
+                __syncthreads();
+                PHNMS_TRACE(5);  // warp-level candidates
+                // 2. CTA-level best M (every warp redundantly; nwarps * M <= 64 entries)
+                u64 ctop[M];
+                {
+                    const int nE = nwarps * M;
+                    const u64 *wt = wtop + (size_t)par_bit * 32 * M;
+                    u64 e0 = lane < nE ? wt[lane] : kNone64, e1 = lane + 32 < nE ? wt[lane + 32] : kNone64;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const u64 b = warp_min_u64(min(e0, e1));
+                        ctop[i] = b;
+                        if (b != kNone64) {
+                            if (e0 == b) e0 = kNone64;
+                            if (e1 == b) e1 = kNone64;
                         }
                     }
                 }
-            }
-            if (best == kNone64 && tid == 0) {  // nothing alive here: an empty slot of the same size
-                if (csize == 1) {
-                    sts_v4(myslot, 0xffffffffu, 0xffffffffu, 0u, 0u);
-                } else {
-                    for (int d = 0; d < csize; ++d) {
-                        const uint32_t dst = mapa_u32(myslot, (uint32_t)d), dbar = mapa_u32(bar_x, (uint32_t)d);
-                        st_async_v4(dst, 0xffffffffu, 0xffffffffu, 0u, 0u, dbar);
-                        for (int g = 0; g < P4 / 4; ++g) st_async_v4(dst + 16 + 16 * g, 0u, 0u, 0u, 0u, dbar);
+                PHNMS_TRACE(6);  // CTA-level candidates
+                // 3. publish candidate i {header, row} into slot[par][rank][i] of every CTA
+                const uint32_t slot_base = smem_u32(slots + (size_t)par_bit * csize * M * L.slot_stride);
+                const uint32_t bar_x = bar_x0 + 8u * par_bit;
+                if (csize > 1 && tid == 0) mbar_arrive_expect_tx(bar_x, (uint32_t)(csize * M * SLOT));
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    int mine = -1;
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+                        if (real[c] && ctop[i] != kNone64 && myK[c] == ctop[i]) mine = i;
+                    if (mine >= 0) {
+                        // the published row carries its 5 header words too (re-read from global memory: this is the
+                        // rare second batch of a frame)
+                        float hdr[5];
+                        const float *grow = p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P;
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) hdr[i] = grow[i];
+#define ROWW(i) ((i) < 5 ? __float_as_uint(hdr[(i) < 5 ? (i) : 0]) : ((i) < P ? __float_as_uint(x[c][(i) >= 5 && (i) < P ? (i) - 5 : 0]) : 0u))
+                        const uint32_t myslot = slot_base + (uint32_t)(((int)rank * M + mine) * L.slot_stride);
+                        const uint32_t khi = (uint32_t)(myK[c] >> 32), klo = (uint32_t)myK[c];
+                        const uint32_t m0 = mb[c][0], m1 = MW > 1 ? mb[c][MW > 1 ? 1 : 0] : 0u, m2 = MW > 2 ? mb[c][MW > 2 ? 2 : 0] : 0u;
+                        if (csize == 1) {
+                            sts_v4(myslot, khi, klo, (uint32_t)st[c], (uint32_t)en[c]);
+                            sts_v4(myslot + 16, m0, m1, m2, 0u);
+#pragma unroll
+                            for (int g = 0; g < P4 / 4; ++g)
+                                sts_v4(myslot + kHdr + 16 * g, ROWW(4 * g), ROWW(4 * g + 1), ROWW(4 * g + 2), ROWW(4 * g + 3));
+                        } else {
+                            for (int d = 0; d < csize; ++d) {
+                                const uint32_t dst = mapa_u32(myslot, (uint32_t)d), dbar = mapa_u32(bar_x, (uint32_t)d);
+                                st_async_v4(dst, khi, klo, (uint32_t)st[c], (uint32_t)en[c], dbar);
+                                st_async_v4(dst + 16, m0, m1, m2, 0u, dbar);
+#pragma unroll
+                                for (int g = 0; g < P4 / 4; ++g)
+                                    st_async_v4(dst + kHdr + 16 * g, ROWW(4 * g), ROWW(4 * g + 1), ROWW(4 * g + 2), ROWW(4 * g + 3), dbar);
+                            }
+                        }
+#undef ROWW
                     }
                 }
-            }
-            (void)owner;
-            if (csize > 1) mbar_wait(bar_x, xphase);
-            else __syncthreads();
-
-            // the winner over the cluster: smallest (key, index) == first not-removed lane in sorted order (:116)
-            u64 wk = kNone64;
-            int wslot = 0;
-            for (int d = 0; d < csize; ++d) {
-                const uint2 h = *reinterpret_cast<const uint2 *>(slots + (size_t)(par_bit * csize + d) * L.slot_stride);
-                const u64 k = ((u64)h.x << 32) | h.y;
-                if (k < wk) { wk = k; wslot = d; }
-            }
-            if (wk == kNone64) break;  // every lane is kept or removed
-            const unsigned char *ws = slots + (size_t)(par_bit * csize + wslot) * L.slot_stride;
-            const int2 sea = *reinterpret_cast<const int2 *>(ws + 8);
-            const uint32_t a_addr = smem_u32(ws + 16);
-            if (rank == 0 && tid == 0) p.keep[(size_t)f * p.N + n] = (long long)(uint32_t)wk;  // :118
-
-            // devIoU(kept lane, my lanes): in-range bitmask per lane, fully unrolled ascending sum (:38-44)
-            uint32_t m[CPT][MW];
-            float dist[CPT];
-            bool act[CPT];
-            int len[CPT];
-            bool any_act = false;
+                if (tid < M) {  // fewer than M alive lanes here: empty slots of the same size
+                    bool empty = false;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int start = max(sea.x, st[c]);   // :31
-                const int end = min(sea.y, en[c]);     // :34 (both clamped to NOFF-1)
-                act[c] = valid[c] && (myK[c] > wk) && (end >= start);  // :36
-                const int i0 = (int)(((uint32_t)start + 5u) & 255u);   // :38 unsigned char counter
-                const int last = (int)((uint32_t)end + 5u);
-                const bool run = act[c] && (i0 <= last);
-                len[c] = (int)((uint32_t)end - (uint32_t)start + 1u);
-#pragma unroll
-                for (int w = 0; w < MW; ++w) {
-                    const int l = max(i0 - 32 * w, 0), h = min(last - 32 * w, 31);
-                    m[c][w] = (run && l <= h) ? ((0xffffffffu >> (31 - h)) & (0xffffffffu << l)) : 0u;
-                }
-                dist[c] = 0.0f;
-                any_act |= run;
-            }
-            if (__any_sync(0xffffffffu, any_act)) {
-#pragma unroll
-                for (int g = 0; g < P4 / 4; ++g) {
-                    const float4 av = lds_v4(a_addr + 16 * g);
-                    const float a4[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = 4 * g + u;
-                        if (i < P) {
-#pragma unroll
-                            for (int c = 0; c < CPT; ++c) {
-                                const float t = __fsub_rn(a4[u], x[c][i]);
-                                if (m[c][i >> 5] & (1u << (i & 31))) dist[c] = __fadd_rn(dist[c], fabsf(t));
+                    for (int i = 0; i < M; ++i)
+                        if (tid == i && ctop[i] == kNone64) empty = true;
+                    if (empty) {
+                        const uint32_t myslot = slot_base + (uint32_t)(((int)rank * M + tid) * L.slot_stride);
+                        if (csize == 1) {
+                            sts_v4(myslot, 0xffffffffu, 0xffffffffu, 0u, 0u);
+                        } else {
+                            for (int d = 0; d < csize; ++d) {
+                                const uint32_t dst = mapa_u32(myslot, (uint32_t)d), dbar = mapa_u32(bar_x, (uint32_t)d);
+                                st_async_v4(dst, 0xffffffffu, 0xffffffffu, 0u, 0u, dbar);
+                                for (int g = 1; g < SLOT / 16; ++g) st_async_v4(dst + 16 * g, 0u, 0u, 0u, 0u, dbar);
                             }
                         }
                     }
                 }
+                PHNMS_TRACE(7);  // published
+                if (csize > 1) {
+                    if (p.trace_len < 0) mbar_wait_watch(bar_x, xphase, p.trace, 2, f, round_ctr);
+                    else mbar_wait(bar_x, xphase);
+                } else {
+                    __syncthreads();
+                }
+                PHNMS_TRACE(8);  // exchange complete
+
+                // 4. merged guaranteed prefix (warp 0): rank every published candidate, keep those not above the bound,
+                //    and copy their headers, in rank order, into the compact array the rounds read
+                sl = slots + (size_t)par_bit * csize * M * L.slot_stride;
+                hb = bh;
+                hs = kHdr;
+                if (warp == 0) {
+                    const int nS = csize * M;
+                    u64 bound = kNone64;
+                    for (int d = 0; d < csize; ++d) {
+                        const uint2 h = *reinterpret_cast<const uint2 *>(sl + (size_t)(d * M + M - 1) * L.slot_stride);
+                        bound = min(bound, ((u64)h.x << 32) | h.y);   // an incomplete list (empty last slot) bounds nothing
+                    }
+                    int nvalid = 0;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int e = lane + 32 * half;
+                        u64 k = kNone64;
+                        uint4 h0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), h1 = make_uint4(0u, 0u, 0u, 0u);
+                        if (e < nS) {
+                            h0 = *reinterpret_cast<const uint4 *>(sl + (size_t)e * L.slot_stride);
+                            h1 = *reinterpret_cast<const uint4 *>(sl + (size_t)e * L.slot_stride + 16);
+                            k = ((u64)h0.x << 32) | h0.y;
+                        }
+                        int rk = 0;
+                        for (int q = 0; q < nS; ++q) {
+                            const uint2 hq = *reinterpret_cast<const uint2 *>(sl + (size_t)q * L.slot_stride);
+                            rk += (((u64)hq.x << 32) | hq.y) < k;
+                        }
+                        const bool ok = k != kNone64 && k <= bound;
+                        if (ok && rk <= lcap) {
+                            h1.w = (uint32_t)e;   // aux: the slot that holds the row
+                            *reinterpret_cast<uint4 *>(bh + (size_t)rk * kHdr) = h0;
+                            *reinterpret_cast<uint4 *>(bh + (size_t)rk * kHdr + 16) = h1;
+                        }
+                        nvalid += __popc(__ballot_sync(0xffffffffu, ok));
+                    }
+                    if (lane == 0) *lcount_p = (uint32_t)min(nvalid, 1 + lcap);
+                    cdead[dead_row * 32 + lane] = 0u;
+                }
+                __syncthreads();
+                PHNMS_TRACE(9);  // merged list ready
+                lcount = (int)*lcount_p;
             }
+            if (lcount == 0) break;  // every lane is kept or removed
+
+            // 5. spare lanes take register copies of candidates 1 .. lcount-1
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-                const bool hit = act[c] && (dist[c] < __fmul_rn(p.thr, (float)len[c]));  // :46
-                if (hit || myK[c] == wk) par[c] = (uint32_t)(n + 1);                      // :127,:129
+                const int v = c * T + tid - p.rpc;
+                if (v >= 0) {
+                    virt[c] = 1 + v < lcount;
+                    myK[c] = kNone64;
+                    if (virt[c]) {
+                        const unsigned char *h = hb + (size_t)(1 + v) * hs;
+                        const uint4 h0 = *reinterpret_cast<const uint4 *>(h);
+                        const uint4 h1 = *reinterpret_cast<const uint4 *>(h + 16);
+                        myK[c] = ((u64)h0.x << 32) | h0.y;
+                        st[c] = (int)h0.z;
+                        en[c] = (int)h0.w;
+                        mb[c][0] = h1.x;
+                        if (MW > 1) mb[c][MW > 1 ? 1 : 0] = h1.y;
+                        if (MW > 2) mb[c][MW > 2 ? 2 : 0] = h1.z;
+                        const float *row = reinterpret_cast<const float *>(sl + (size_t)(fb ? 1 + v : (int)h1.w) * L.slot_stride + kHdr);
+#pragma unroll
+                        for (int i = 0; i < NOFF; ++i) x[c][i] = row[5 + i];
+                        par[c] = 0u;
+                    }
+                }
             }
-            ++n;
-            if (n == p.top_k) break;  // :133 (top_k == 0 never stops early)
+            PHNMS_TRACE(10);  // spare lanes loaded
+
+            // 6. one round per alive candidate of the prefix, in rank order
+            for (int j = 0; j < lcount; ++j) {
+                if (j > 0 && cdead[dead_row * 32 + j] != 0u) continue;  // suppressed by an earlier winner of this batch
+                const unsigned char *h = hb + (size_t)j * hs;
+                const uint4 wh = *reinterpret_cast<const uint4 *>(h);
+                const uint4 wm = *reinterpret_cast<const uint4 *>(h + 16);
+                const u64 wk = ((u64)wh.x << 32) | wh.y;
+                const int sa = (int)wh.z, ea = (int)wh.w;
+                const unsigned char *arow_b = sl + (size_t)(fb ? j : (int)wm.w) * L.slot_stride + kHdr;
+                const uint32_t a_addr = smem_u32(arow_b);
+                if (rank == 0 && tid == 0) p.keep[(size_t)f * p.N + n] = (long long)(uint32_t)wk;  // :118
+
+                // devIoU(kept lane, my lanes): in-range bitmask per lane, fully unrolled ascending sum (:38-44).
+                // [max(sa,sb), min(ea,eb)] is the intersection of the two lanes' own ranges, so the pair's bitmask is
+                // the AND of the two per-lane bitmasks (both precomputed) -- unless BOTH starts are below -5, where the
+                // reference's unsigned-char counter wraps (rare; recomputed from the wrapped counter).
+                const uint32_t ma[3] = {wm.x, wm.y, wm.z};
+                uint32_t m[CPT][MW];
+                float dist[CPT];
+                bool act[CPT];
+                int len[CPT];
+                bool any_act = false;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int start = max(sa, st[c]);   // :31
+                    const int end = min(ea, en[c]);     // :34 (both clamped to NOFF-1)
+                    act[c] = (real[c] || virt[c]) && (myK[c] > wk) && (end >= start);  // :36
+                    len[c] = (int)((uint32_t)end - (uint32_t)start + 1u);
+#pragma unroll
+                    for (int w = 0; w < MW; ++w) m[c][w] = act[c] ? (ma[w] & mb[c][w]) : 0u;
+                    if (act[c] && start < -5) {            // :38 unsigned char counter wrapped: (5 + start) & 255
+                        const int i0 = (int)(((uint32_t)start + 5u) & 255u), last = (int)((uint32_t)end + 5u);
+                        const bool run = i0 <= last;       // then 0 <= last <= NOFF+4: nothing below can wrap
+#pragma unroll
+                        for (int w = 0; w < MW; ++w) {
+                            const int l = max(i0 - 32 * w, 0), hh = min((run ? last : -1) - 32 * w, 31);
+                            m[c][w] = (run && l <= hh) ? ((0xffffffffu >> (31 - hh)) & (0xffffffffu << l)) : 0u;
+                        }
+                    }
+                    dist[c] = 0.0f;
+                    any_act |= act[c];
+                }
+                PHNMS_TRACE(14);  // round set-up
+                if (__any_sync(0xffffffffu, any_act)) {
+                    // rare: a start in [-5,-1] pulls header columns 0..4 into the sum (:38); they come first
+                    bool hdr_terms = false;
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) hdr_terms |= (m[c][0] & 0x1fu) != 0u;
+                    if (__any_sync(0xffffffffu, hdr_terms)) {
+                        const float *arow = reinterpret_cast<const float *>(arow_b);
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            if (m[c][0] & 0x1fu) {
+                                const int v = c * T + tid - p.rpc;
+                                const float *mine_hdr;
+                                if (real[c]) {
+                                    mine_hdr = p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P;
+                                } else {
+                                    const int sidx = fb ? 1 + v : (int)reinterpret_cast<const uint32_t *>(hb + (size_t)(1 + v) * hs)[7];
+                                    mine_hdr = reinterpret_cast<const float *>(sl + (size_t)sidx * L.slot_stride + kHdr);
+                                }
+                                for (int i = 0; i < 5; ++i)
+                                    if (m[c][0] & (1u << i)) dist[c] = __fadd_rn(dist[c], fabsf(__fsub_rn(arow[i], mine_hdr[i])));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int g = 1; g < P4 / 4; ++g) {
+                        const float4 av = lds_v4(a_addr + 16 * g);
+                        const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = 4 * g + u;
+                            if (i >= 5 && i < P) {
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c) {
+                                    const float t = __fsub_rn(a4[u], x[c][i - 5]);
+                                    if (m[c][i >> 5] & (1u << (i & 31))) dist[c] = __fadd_rn(dist[c], fabsf(t));
+                                }
+                            }
+                        }
+                    }
+                }
+                PHNMS_TRACE(15);  // offset loop
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const bool hit = act[c] && (dist[c] < __fmul_rn(p.thr, (float)len[c]));  // :46
+                    if (hit || myK[c] == wk) par[c] = (uint32_t)(n + 1);                      // :127,:129
+                    // A suppressed candidate is flagged for the LATER round that would have picked it (read after at
+                    // least one barrier).  The winner's own copy must not touch its flag: slower warps may not have
+                    // read it yet at the top of THIS round (that race skipped the round in some warps -> hang).
+                    if (virt[c] && hit) cdead[dead_row * 32 + 1 + (c * T + tid - p.rpc)] = 1u;
+                }
+                ++n;
+                PHNMS_TRACE(11);  // round done
+                if (n == p.top_k) {  // :133 (top_k == 0 never stops early)
+                    frame_done = true;
+                    break;
+                }
+                __syncthreads();  // candidate-dead flags of this round are visible to the next
+                PHNMS_TRACE(12);  // round barrier
+            }
         }
 
         // ---- outputs, written once: parent, zero padding of keep, count ------------------------------------------
@@ -362,7 +623,9 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             }
             if (rank == 0 && tid == 0) p.num_keep[f] = p.top_k < n ? p.top_k : n;  // :142
         }
+        PHNMS_TRACE(13);  // outputs written
         cur = nxt;
+        fpar ^= 1u;
     }
 
     if (csize > 1) {  // no CTA leaves while a peer may still address its shared memory

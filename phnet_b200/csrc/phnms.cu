@@ -6,10 +6,12 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "fused_nms.cuh"
 #include "fused_reg.cuh"
 #include "tiled_nms.cuh"
+#include "topm.cuh"
 
 using namespace phnms;
 
@@ -55,6 +57,7 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
     pl->launches = 1;
     pl->variant = 0;
     pl->cols_per_thread = 1;
+    pl->max_active_clusters = 0;
     const int cand[5] = {1, 2, 4, 8, 16};
 
     auto rows_for = [&](int c) {
@@ -106,6 +109,8 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
                 pl->rows_per_cta = rpc;
                 pl->smem_bytes = L.total;
                 pl->grid = (int)(clusters * csize);
+                pl->launches = 2;  // phnms_topm_kernel + phnms_freg_kernel
+                pl->workspace_bytes = (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 256;   // candidate block per frame
                 return PHNMS_OK;
             }
             if (t.variant == PHNMS_FUSED_REG) return PHNMS_ERR_TUNING;
@@ -169,27 +174,86 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
     return PHNMS_OK;
 }
 
-template <typename Kern, typename... Args>
-int launch_cluster(Kern kern, const phnms_plan &pl, cudaStream_t stream, Args... args) {
+template <typename Kern>
+int configure_cluster(Kern kern, const phnms_plan &pl, cudaStream_t stream, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return (int)e;
     if (pl.cluster > 8) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return (int)e;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)pl.grid);
-    cfg.blockDim = dim3((unsigned)pl.threads);
-    cfg.dynamicSmemBytes = (size_t)pl.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3((unsigned)pl.grid);
+    cfg->blockDim = dim3((unsigned)pl.threads);
+    cfg->dynamicSmemBytes = (size_t)pl.smem_bytes;
+    cfg->stream = stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)pl.cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+    return 0;
+}
+
+template <typename Kern, typename... Args>
+int launch_cluster(Kern kern, const phnms_plan &pl, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int rc = configure_cluster(kern, pl, stream, &cfg, attr);
+    if (rc) return rc;
     return (int)cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+template <typename Kern>
+int occupancy_clusters(Kern kern, phnms_plan pl) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    pl.grid = pl.cluster * 4096;
+    if (configure_cluster(kern, pl, nullptr, &cfg, attr)) return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fused_occupancy_query(const phnms_plan &pl, int n_off);
+
+// Resident clusters for this launch shape (cudaOccupancyMaxActiveClusters).  The persistent grid must not exceed it:
+// a cluster that is not resident only starts when another one has finished ALL of its frames (a second full wave).
+// The answer depends only on (device, kernel, cluster, threads, smem); the last one is remembered per host thread.
+int fused_occupancy(const phnms_plan &pl, int n_off) {
+    if (pl.path != PHNMS_PATH_FUSED) return 0;
+    struct Key { int dev, variant, n_off, cluster, threads, smem, cpt, occ; };
+    static thread_local Key last = {-1, 0, 0, 0, 0, 0, 0, 0};
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (last.dev == dev && last.variant == pl.variant && last.n_off == n_off && last.cluster == pl.cluster &&
+        last.threads == pl.threads && last.smem == pl.smem_bytes && last.cpt == pl.cols_per_thread)
+        return last.occ;
+    const int occ = fused_occupancy_query(pl, n_off);
+    last = Key{dev, pl.variant, n_off, pl.cluster, pl.threads, pl.smem_bytes, pl.cols_per_thread, occ};
+    return occ;
+}
+
+void fit_grid_to_occupancy(phnms_plan *pl, int64_t F, int n_off, const phnms_tuning *tun) {
+    if (pl->path != PHNMS_PATH_FUSED) return;
+    const int occ = fused_occupancy(*pl, n_off);
+    pl->max_active_clusters = occ;
+    if (occ <= 0) return;
+    long long clusters = occ;
+    if (tun && tun->max_clusters > 0 && clusters > tun->max_clusters) clusters = tun->max_clusters;
+    if (clusters > F) clusters = F;
+    if (clusters < 1) clusters = 1;
+    pl->grid = (int)(clusters * pl->cluster);
+}
+
+int fused_occupancy_query(const phnms_plan &pl, int n_off) {
+    if (pl.variant == PHNMS_FUSED_REG) {
+        if (n_off == 72) return occupancy_clusters(phnms_freg_kernel<72, 1>, pl);
+        if (pl.cols_per_thread == 1) return occupancy_clusters(phnms_freg_kernel<36, 1>, pl);
+        return occupancy_clusters(phnms_freg_kernel<36, 2>, pl);
+    }
+    return occupancy_clusters(phnms_fused_kernel, pl);
 }
 
 }  // namespace
@@ -226,7 +290,9 @@ int phnms_plan_query(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning
     if (rc != PHNMS_OK) return rc;
     DeviceInfo dev;
     const bool have_dev = device_info(&dev) == 0;
-    return make_plan(F, N, n_off, tuning, have_dev ? &dev : nullptr, plan);
+    rc = make_plan(F, N, n_off, tuning, have_dev ? &dev : nullptr, plan);
+    if (rc == PHNMS_OK && have_dev && dev.cc_major == 10) fit_grid_to_occupancy(plan, F, n_off, tuning);
+    return rc;
 }
 
 size_t phnms_order_workspace_bytes(int64_t F, int64_t N) {
@@ -250,6 +316,14 @@ int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int6
 int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                       float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
                       void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_) {
+    return phnms_forward_f32_trace(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent,
+                                   ws, ws_bytes, tuning, stream_, nullptr, 0);
+}
+
+int phnms_forward_f32_trace(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
+                            int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
+                            int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_,
+                            int64_t *trace, int trace_len) {
     int rc = check_shape(F, N, n_off);
     if (rc != PHNMS_OK) return rc;
     if (sort_model < 0 || sort_model > 2 || top_k < 0) return PHNMS_ERR_BAD_ARG;
@@ -268,6 +342,7 @@ int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_
     phnms_plan pl;
     rc = make_plan(F, N, n_off, tuning, &dev, &pl);
     if (rc != PHNMS_OK) return rc;
+    if (F > 1) fit_grid_to_occupancy(&pl, F, n_off, tuning);
 
     if (pl.path == PHNMS_PATH_FUSED) {
         FusedParams fp;
@@ -286,7 +361,17 @@ int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_
         fp.sort_model = sort_model;
         fp.thr = thresh;
         fp.L = fused_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
+        fp.trace = reinterpret_cast<long long *>(trace);
+        fp.trace_len = trace_len;
+        fp.topm = nullptr;
         if (pl.variant == PHNMS_FUSED_REG) {
+            if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
+            int *topm = reinterpret_cast<int *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+            phnms_topm_kernel<<<(unsigned)((F + kTopmWarps - 1) / kTopmWarps), kTopmWarps * 32, 0, stream>>>(
+                props, scores, n_valid, F, (int)N, n_off, sort_model, topm);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+            fp.topm = getenv("PHNMS_NO_TOPM") ? nullptr : topm;   // debugging aid: force in-kernel candidate selection
             const FregLayout RL = freg_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
             if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1>, pl, stream, fp, RL);
             if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1>, pl, stream, fp, RL);

@@ -40,7 +40,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        r = {"variant": v, "cluster": c, "threads": t, "rows_per_cta": plan["rows_per_cta"], "smem": plan["smem_bytes"], "grid": plan["grid"],
+        r = {"variant": v, "cluster": c, "threads": t, "rows_per_cta": plan["rows_per_cta"], "smem": plan["smem_bytes"], "grid": plan["grid"], "occ": plan["max_active_clusters"],
              "ms": round(ms, 4), "Mframes_s": round(F / ms / 1e3, 3), "GBs": round(F * bpf / ms / 1e6, 1),
              "frac": round(F * bpf / ms / 1e6 / 6554.2, 4)}
         res.append(r)
