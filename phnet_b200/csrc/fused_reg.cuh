@@ -38,6 +38,7 @@ struct FregLayout {
     int off_slots;    // 2 parities x csize x kCand exchange slots
     int slot_stride;  // kHdr + 4 * round4(P)
     int off_pslots;   // 2 frame parities x kTopM slots: precomputed candidates of the current / next frame
+    int off_sbuf;     // 2 frame parities x rpc scores (this CTA's slice), filled by cp.async one frame ahead
     int off_rows;     // staging: 16 B lead + rpc*P*4 + pad
     int total;
 };
@@ -57,6 +58,8 @@ inline FregLayout freg_layout(int rpc, int P, int csize) {
     o += 2 * csize * kCand * L.slot_stride;
     L.off_pslots = o;
     o += 2 * kTopM * L.slot_stride;
+    L.off_sbuf = o;
+    o += 2 * round_up(rpc * 4, 16);
     L.off_rows = o;
     o += 16 + round_up(rpc * P * 4, 16) + 32;
     L.total = o;
@@ -77,6 +80,12 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Bits [5+start, 5+end] of one lane's own offset range (start below -5 acts as "no lower bound": the other lane's
 // start wins the max).  Bit i corresponds to row word i (columns 0..4 are the header, nms_kernel.cu:38).
 template <int MW>
@@ -90,7 +99,7 @@ __device__ __forceinline__ void range_mask(int start, int end, uint32_t (&m)[MW]
     }
 }
 
-struct Slab {       // what one CTA loads for one frame
+struct Slab {       // what one CTA loads for one frame (a pure function of the frame index: recomputed, not carried)
     int nv;         // real proposals in the frame
     int r0;         // first row owned by this CTA
     int nloc;       // rows owned
@@ -98,26 +107,37 @@ struct Slab {       // what one CTA loads for one frame
     bool bulk;      // a TMA bulk copy is in flight for it
 };
 
-// Requests frame f's slab: TMA bulk copy of the 16-byte aligned body (completes on `bar`), the <= 3 unaligned words at
-// either end by ordinary loads.  Call with the staging buffer free (after a __syncthreads that follows its last read).
-// When phnms_topm_kernel ran, the frame's candidate block (kTopM slots, laid out exactly like pslots) rides along as
-// one more bulk copy on the same mbarrier.
-__device__ __forceinline__ Slab request_slab(const FusedParams &p, long long f, uint32_t rank, unsigned char *rows_buf,
-                                             uint32_t bar, int tid, int T, int P, unsigned char *cand_dst,
-                                             uint32_t cand_bytes) {
+__device__ __forceinline__ Slab slab_geometry(const FusedParams &p, long long f, uint32_t rank, int P) {
     Slab s;
     s.nv = p.N;
     if (p.n_valid) s.nv = max(0, min(p.n_valid[f], p.N));
     s.r0 = min((int)rank * p.rpc, s.nv);
     s.nloc = min(p.rpc, s.nv - s.r0);
+    const uintptr_t b = (uintptr_t)(p.props + ((size_t)f * p.N + s.r0) * P), e = b + (size_t)s.nloc * P * 4;
+    const uintptr_t b_al = (b + 15) & ~(uintptr_t)15, e_al = e & ~(uintptr_t)15;
+    const bool body = e_al > b_al;
+    s.bulk = body || p.topm != nullptr;
+    s.head = body ? (int)(b_al - b) : 0;
+    return s;
+}
+
+// Requests frame f's slab: TMA bulk copy of the 16-byte aligned body (completes on `bar`), the <= 3 unaligned words at
+// either end by ordinary loads.  Call with the staging buffer free (after a __syncthreads that follows its last read).
+// When phnms_topm_kernel ran, the frame's candidate block (kTopM slots, laid out exactly like pslots) rides along as
+// one more bulk copy on the same mbarrier.
+__device__ __forceinline__ void request_slab(const FusedParams &p, long long f, uint32_t rank, unsigned char *rows_buf,
+                                             uint32_t bar, int tid, int T, int P, unsigned char *cand_dst,
+                                             uint32_t cand_bytes, float *sbuf) {
+    const Slab s = slab_geometry(p, f, rank, P);
     const float *src = p.props + ((size_t)f * p.N + s.r0) * P;
     const uintptr_t b = (uintptr_t)src, e = b + (size_t)s.nloc * P * 4;
     const uintptr_t b_al = (b + 15) & ~(uintptr_t)15, e_al = e & ~(uintptr_t)15;
     const bool body = e_al > b_al;
     const bool cand = p.topm != nullptr;
-    s.bulk = body || cand;
-    s.head = body ? (int)(b_al - b) : 0;
     float *rows = reinterpret_cast<float *>(rows_buf + 16 - s.head);
+    // this CTA's slice of the scores: asynchronous 4-byte copies (no register is tied up while they are in flight)
+    for (int c = tid; c < s.nloc; c += T) cp_async_4(smem_u32(sbuf + c), p.scores + (size_t)f * p.N + s.r0 + c);
+    cp_async_commit();
     if (cand) {
         const uint32_t slab_bytes = body ? (uint32_t)(e_al - b_al) : 0u;
         if (tid == 0) mbar_arrive_expect_tx(bar, slab_bytes + cand_bytes);
@@ -150,18 +170,17 @@ __device__ __forceinline__ Slab request_slab(const FusedParams &p, long long f, 
     } else {
         for (int w = tid; w < s.nloc * P; w += T) rows[w] = src[w];
     }
-    return s;
 }
 
 #define PHNMS_TRACE(tag)                                                                      \
     do {                                                                                      \
-        if (p.trace && p.trace_len > 0 && blockIdx.x == 0 && tid == 0 && tcount + 1 < p.trace_len) { \
+        if (kTrace && p.trace && p.trace_len > 0 && blockIdx.x == 0 && tid == 0 && tcount + 1 < p.trace_len) { \
             p.trace[tcount++] = (long long)(tag);                                             \
             p.trace[tcount++] = clock64();                                                    \
         }                                                                                     \
     } while (0)
 
-template <int NOFF, int CPT>
+template <int NOFF, int CPT, bool kTrace>
 __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p, const FregLayout L) {
     constexpr int P = 5 + NOFF;
     constexpr int MW = (P + 31) / 32;   // in-range bitmask words (<= 3)
@@ -185,6 +204,8 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
     unsigned char *slots = smem + L.off_slots;
     unsigned char *pslots = smem + L.off_pslots;
     unsigned char *rows_buf = smem + L.off_rows;
+    float *sbuf = reinterpret_cast<float *>(smem + L.off_sbuf);
+    const int sbuf_stride = round_up(p.rpc * 4, 16) / 4;
     const uint32_t bar_load = smem_u32(smem), bar_x0 = bar_load + 8;
 
     if (tid == 0) {
@@ -201,30 +222,26 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
 
     uint32_t load_phase = 0, round_ctr = 0, fpar = 0;
     int tcount = 0;
-    float sc[CPT];       // this frame's scores of my columns
-    Slab cur;
-    if (cl < p.F) {
-        cur = request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(kTopM * SLOT));
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int col = c * T + tid;
-            sc[c] = col < cur.nloc ? p.scores[(size_t)cl * p.N + cur.r0 + col] : 0.0f;
-        }
-    }
+    (void)tcount;
+    if (cl < p.F) request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(kTopM * SLOT), sbuf);
     // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
     // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
     const int lcap = min(T * CPT - p.rpc, 31);
 
     for (long long f = cl; f < p.F; f += ncl) {
         PHNMS_TRACE(1);  // frame start
-        if (warp == 0) cdead[2 * 32 + lane] = 0u;            // dead flags of the first batch
         // ---- staging -> registers -------------------------------------------------------------------------------
+        const Slab cur = slab_geometry(p, f, rank, P);
         if (cur.bulk) {
-            if (p.trace_len < 0) mbar_wait_watch(bar_load, load_phase, p.trace, 1, f, round_ctr);
+            if (kTrace && p.trace_len < 0) mbar_wait_watch(bar_load, load_phase, p.trace, 1, f, round_ctr);
             else mbar_wait(bar_load, load_phase);
             load_phase ^= 1u;
         }
+        cp_async_wait_all();   // my own score copies (each thread reads back only what it copied itself)
         __syncthreads();
+        // Dead flags of the first batch.  Reset only here, between the frame's two barriers: before the first one a slower
+        // warp can still be inside the previous frame's last round (reading or setting these flags).
+        if (warp == 0) cdead[2 * 32 + lane] = 0u;
         PHNMS_TRACE(2);  // slab landed
         const float *rows = reinterpret_cast<const float *>(rows_buf + 16 - cur.head);
         const int nv = cur.nv, r0 = cur.r0, nloc = cur.nloc;
@@ -242,14 +259,14 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             for (int i = 0; i < NOFF; ++i) x[c][i] = row[5 + i];
             st[c] = lane_start(row[2], NOFF);            // nms_kernel.cu:29-30
             en[c] = lane_end(row[4], st[c], NOFF);       // :32-34
-            key[c] = key_desc(sc[c], p.sort_model == 1);
+            key[c] = key_desc(real[c] ? sbuf[fpar * sbuf_stride + col] : 0.0f, p.sort_model == 1);
             par[c] = 0u;
             range_mask<MW>(st[c], en[c], mb[c]);
         }
         const bool bitonic = (p.sort_model == 0) && nv <= 32 && nv >= 2;  // torch: unstable bitonic network (n <= 32)
         if (bitonic && warp == 0 && nloc > 0) {  // rank 0 holds the whole frame (rows_per_cta >= 32), column == lane
             bit_ok[lane] = lane < nv;
-            bit_key[lane] = lane < nv ? sc[0] : 0.0f;
+            bit_key[lane] = lane < nv ? sbuf[fpar * sbuf_stride + lane] : 0.0f;
             bit_val[lane] = lane < nv ? lane : 0;
             __syncwarp();
             for (unsigned size = 2; size <= 32; size *= 2) {
@@ -279,18 +296,10 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         PHNMS_TRACE(3);  // rows in registers
 
         // ---- request the next frame now; it lands while this frame's rounds run ----------------------------------
-        Slab nxt;
-        nxt.bulk = false; nxt.nv = nxt.r0 = nxt.nloc = nxt.head = 0;
-        const long long fn = f + ncl;
-        if (fn < p.F) {
-            nxt = request_slab(p, fn, rank, rows_buf, bar_load, tid, T, P,
-                               pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(kTopM * SLOT));
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int col = c * T + tid;
-                sc[c] = col < nxt.nloc ? p.scores[(size_t)fn * p.N + nxt.r0 + col] : 0.0f;
-            }
-        }
+        if (f + ncl < p.F)
+            request_slab(p, f + ncl, rank, rows_buf, bar_load, tid, T, P,
+                         pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(kTopM * SLOT),
+                         sbuf + (fpar ^ 1u) * sbuf_stride);
         PHNMS_TRACE(4);  // next slab requested
 
         u64 myK[CPT];
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
                 }
                 PHNMS_TRACE(7);  // published
                 if (csize > 1) {
-                    if (p.trace_len < 0) mbar_wait_watch(bar_x, xphase, p.trace, 2, f, round_ctr);
+                    if (kTrace && p.trace_len < 0) mbar_wait_watch(bar_x, xphase, p.trace, 2, f, round_ctr);
                     else mbar_wait(bar_x, xphase);
                 } else {
                     __syncthreads();
@@ -624,7 +633,6 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             if (rank == 0 && tid == 0) p.num_keep[f] = p.top_k < n ? p.top_k : n;  // :142
         }
         PHNMS_TRACE(13);  // outputs written
-        cur = nxt;
         fpar ^= 1u;
     }
 

@@ -249,9 +249,9 @@ void fit_grid_to_occupancy(phnms_plan *pl, int64_t F, int n_off, const phnms_tun
 
 int fused_occupancy_query(const phnms_plan &pl, int n_off) {
     if (pl.variant == PHNMS_FUSED_REG) {
-        if (n_off == 72) return occupancy_clusters(phnms_freg_kernel<72, 1>, pl);
-        if (pl.cols_per_thread == 1) return occupancy_clusters(phnms_freg_kernel<36, 1>, pl);
-        return occupancy_clusters(phnms_freg_kernel<36, 2>, pl);
+        if (n_off == 72) return occupancy_clusters(phnms_freg_kernel<72, 1, false>, pl);
+        if (pl.cols_per_thread == 1) return occupancy_clusters(phnms_freg_kernel<36, 1, false>, pl);
+        return occupancy_clusters(phnms_freg_kernel<36, 2, false>, pl);
     }
     return occupancy_clusters(phnms_fused_kernel, pl);
 }
@@ -367,15 +367,29 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
         if (pl.variant == PHNMS_FUSED_REG) {
             if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
             int *topm = reinterpret_cast<int *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-            phnms_topm_kernel<<<(unsigned)((F + kTopmWarps - 1) / kTopmWarps), kTopmWarps * 32, 0, stream>>>(
-                props, scores, n_valid, F, (int)N, n_off, sort_model, topm);
+            {
+                int warps = kTopmWarps;
+                while (warps > 1 && topm_smem_bytes((int)N, warps) > 160 * 1024) warps >>= 1;
+                const size_t sm = topm_smem_bytes((int)N, warps);
+                if (sm > 48 * 1024) {
+                    cudaError_t e2 = cudaFuncSetAttribute(phnms_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                    if (e2 != cudaSuccess) return (int)e2;
+                }
+                phnms_topm_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(
+                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm);
+            }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             fp.topm = getenv("PHNMS_NO_TOPM") ? nullptr : topm;   // debugging aid: force in-kernel candidate selection
             const FregLayout RL = freg_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
-            if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1>, pl, stream, fp, RL);
-            if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1>, pl, stream, fp, RL);
-            return launch_cluster(phnms_freg_kernel<36, 2>, pl, stream, fp, RL);
+            if (trace) {   // profiling / watchdog build of the same kernel
+                if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1, true>, pl, stream, fp, RL);
+                if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1, true>, pl, stream, fp, RL);
+                return launch_cluster(phnms_freg_kernel<36, 2, true>, pl, stream, fp, RL);
+            }
+            if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1, false>, pl, stream, fp, RL);
+            if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1, false>, pl, stream, fp, RL);
+            return launch_cluster(phnms_freg_kernel<36, 2, false>, pl, stream, fp, RL);
         }
         return launch_cluster(phnms_fused_kernel, pl, stream, fp);
     }

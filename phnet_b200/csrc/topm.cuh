@@ -14,16 +14,21 @@ namespace phnms {
 
 constexpr int kTopmWarps = 4;
 
+// dynamic shared memory: per warp 33 * ceil(N / 32) u32 keys, stored group-major ([i % 32][i / 32], row pitch G+1... see
+// kidx) so that both the owner lane's column walk and the warp's row walk of one group are bank-conflict free.
+inline size_t topm_smem_bytes(int N, int warps) { return (size_t)warps * 32 * (((N + 31) / 32) | 1) * 4; }
+
 __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float *__restrict__ props,
                                                                     const float *__restrict__ scores,
                                                                     const int32_t *__restrict__ n_valid, long long F,
                                                                     int N, int n_off, int sort_model,
                                                                     int *__restrict__ topm) {
+    extern __shared__ __align__(16) unsigned char smem_topm[];
     __shared__ float bit_key[kTopmWarps][32];
     __shared__ int bit_val[kTopmWarps][32];
     __shared__ int bit_ok[kTopmWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long f = (long long)blockIdx.x * kTopmWarps + warp;
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (f >= F) return;
     int n = N;
     if (n_valid) n = max(0, min(n_valid[f], N));
@@ -57,37 +62,37 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
         }
         if (lane < n) mine = ((u64)(uint32_t)lane << 32) | (uint32_t)bv[lane];  // the sorted position is the rank key
     } else {
+        // Warp-level select of the kTopM smallest rank keys.  Lane l owns "group l" = proposals l, l+32, l+64, ...;
+        // it keeps the group's smallest not-yet-picked key in a register.  Per pick: one warp arg-min over the 32 group
+        // minima, then the whole warp rescans the winning group (one key per lane) for its next minimum.
         const bool nan_first = sort_model == 1;
-        constexpr int kRegs = 32;  // frames of up to 1024 proposals keep their keys in registers
-        uint32_t kreg[kRegs];
-        const bool in_regs = n <= 32 * kRegs;
-        if (in_regs) {
-#pragma unroll
-            for (int q = 0; q < kRegs; ++q) {
-                const int i = lane + 32 * q;
-                kreg[q] = i < n ? key_desc(sc[i], nan_first) : 0xffffffffu;
+        const int G = (N + 31) / 32, pitch = G | 1;   // odd pitch: conflict-free both ways
+        uint32_t *kb = reinterpret_cast<uint32_t *>(smem_topm) + (size_t)warp * 32 * pitch;
+        u64 gmin = kNone64;
+        for (int q = 0; q < G; ++q) {
+            const int i = lane + 32 * q;
+            uint32_t k = 0xffffffffu;
+            if (i < n) {
+                k = key_desc(sc[i], nan_first);
+                const u64 K = ((u64)k << 32) | (uint32_t)i;
+                gmin = min(gmin, K);
             }
+            kb[lane * pitch + q] = k;
         }
-        u64 prev = 0;
+        __syncwarp();
         for (int j = 0; j < kTopM; ++j) {
-            u64 best = kNone64;
-            if (in_regs) {
-#pragma unroll
-                for (int q = 0; q < kRegs; ++q) {
-                    const int i = lane + 32 * q;
-                    const u64 K = ((u64)kreg[q] << 32) | (uint32_t)i;
-                    if (i < n && (j == 0 || K > prev) && K < best) best = K;
-                }
-            } else {
-                for (int i = lane; i < n; i += 32) {
-                    const u64 K = ((u64)key_desc(sc[i], nan_first) << 32) | (uint32_t)i;
-                    if ((j == 0 || K > prev) && K < best) best = K;
-                }
-            }
-            best = warp_min_u64(best);
+            const u64 best = warp_min_u64(gmin);
             if (best == kNone64) break;
-            prev = best;
             if (lane == j) mine = best;
+            const int g = (int)((uint32_t)best & 31u);       // the group (== lane) that owned the pick
+            u64 cand = kNone64;
+            for (int q = lane; q < G; q += 32) {              // rescan group g: proposal g + 32 q
+                const int i = g + 32 * q;
+                const u64 K = ((u64)kb[g * pitch + q] << 32) | (uint32_t)i;
+                if (i < n && K > best) cand = min(cand, K);
+            }
+            cand = warp_min_u64(cand);
+            if (lane == g) gmin = cand;
         }
     }
 

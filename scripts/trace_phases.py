@@ -24,7 +24,7 @@ for it in range(3):
 torch.cuda.synchronize()
 t = trace.cpu().tolist()
 ev = [(t[i], t[i + 1]) for i in range(0, TL - 1, 2) if t[i] != 0]
-names = {1: "frame start", 2: "wait slab (+sync)", 3: "fill regs (+bitonic, sync)", 4: "request next slab", 5: "warp top-M (+sync)",
+names = {1: "frame start", 2: "wait slab (+sync)", 3: "fill regs (+bitonic, sync)", 4: "prefetch next scores", 16: "request next slab (TMA issue)", 5: "warp top-M (+sync)",
          6: "CTA top-M", 7: "publish", 8: "exchange wait", 9: "merge (+sync)", 10: "spare-lane load", 11: "round tail", 14: "round set-up", 15: "round offset loop",
          12: "round barrier", 13: "outputs"}
 tot = collections.defaultdict(int); cnt = collections.defaultdict(int)
