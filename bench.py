@@ -333,7 +333,8 @@ def run_ours(a):
                        "plan": plan},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(N, n_off, F), "peak_source": peak_src,
-                         "algorithmic_bytes_per_frame": bpf, "kernel": "phnms_fused_kernel" if plan["path"] == 1 else "phnms_mask_kernel",
+                         "algorithmic_bytes_per_frame": bpf, "kernel": ("phnms_topm_kernel + phnms_freg_kernel (one C-ABI call; freg is >90 % of it, profiles/)" if plan.get("variant") == 2
+                                    else "phnms_fused_kernel" if plan["path"] == 1 else "phnms_order/mask/scan kernels"),
                          "kernel_ms_per_launch": kern_ms},
             "clocks": clocks.summary(),
             "gpu_launches": a.steps * plan["launches"],

@@ -69,15 +69,35 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
         const int G = (N + 31) / 32, pitch = G | 1;   // odd pitch: conflict-free both ways
         uint32_t *kb = reinterpret_cast<uint32_t *>(smem_topm) + (size_t)warp * 32 * pitch;
         u64 gmin = kNone64;
-        for (int q = 0; q < G; ++q) {
-            const int i = lane + 32 * q;
-            uint32_t k = 0xffffffffu;
-            if (i < n) {
-                k = key_desc(sc[i], nan_first);
-                const u64 K = ((u64)k << 32) | (uint32_t)i;
-                gmin = min(gmin, K);
+        if (G <= 32) {   // up to 1024 proposals: all score loads are issued before the first one is consumed
+            float sv[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int i = lane + 32 * q;
+                sv[q] = (q < G && i < n) ? sc[i] : 0.0f;
             }
-            kb[lane * pitch + q] = k;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int i = lane + 32 * q;
+                if (q < G) {
+                    uint32_t k = 0xffffffffu;
+                    if (i < n) {
+                        k = key_desc(sv[q], nan_first);
+                        gmin = min(gmin, ((u64)k << 32) | (uint32_t)i);
+                    }
+                    kb[lane * pitch + q] = k;
+                }
+            }
+        } else {
+            for (int q = 0; q < G; ++q) {
+                const int i = lane + 32 * q;
+                uint32_t k = 0xffffffffu;
+                if (i < n) {
+                    k = key_desc(sc[i], nan_first);
+                    gmin = min(gmin, ((u64)k << 32) | (uint32_t)i);
+                }
+                kb[lane * pitch + q] = k;
+            }
         }
         __syncwarp();
         for (int j = 0; j < kTopM; ++j) {
@@ -119,14 +139,34 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
         out[0] = h0;
         out[1] = h1;
     }
-    for (int j = 0; j < kTopM; ++j) {   // rows: the warp copies row j with coalesced loads and stores
-        const u64 kj = __shfl_sync(0xffffffffu, mine, j);
-        float *dst = reinterpret_cast<float *>(blk + (size_t)j * slot_words + 8);
-        if (kj == kNone64) {
-            for (int i = lane; i < P4; i += 32) dst[i] = 0.0f;
-        } else {
-            const float *row = props + ((size_t)f * N + (uint32_t)kj) * P;
-            for (int i = lane; i < P4; i += 32) dst[i] = i < P ? row[i] : 0.0f;
+    // rows: the warp copies row j with coalesced loads and stores; all loads are issued before the first store
+    if (P4 <= 96) {
+        float rv[kTopM][3];
+#pragma unroll
+        for (int j = 0; j < kTopM; ++j) {
+            const u64 kj = __shfl_sync(0xffffffffu, mine, j);
+            const float *row = props + ((size_t)f * N + (kj == kNone64 ? 0u : (uint32_t)kj)) * P;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int i = lane + 32 * t;
+                rv[j][t] = (kj != kNone64 && i < P) ? row[i] : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kTopM; ++j) {
+            float *dst = reinterpret_cast<float *>(blk + (size_t)j * slot_words + 8);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int i = lane + 32 * t;
+                if (i < P4) dst[i] = rv[j][t];
+            }
+        }
+    } else {
+        for (int j = 0; j < kTopM; ++j) {
+            const u64 kj = __shfl_sync(0xffffffffu, mine, j);
+            float *dst = reinterpret_cast<float *>(blk + (size_t)j * slot_words + 8);
+            const float *row = props + ((size_t)f * N + (kj == kNone64 ? 0u : (uint32_t)kj)) * P;
+            for (int i = lane; i < P4; i += 32) dst[i] = (kj != kNone64 && i < P) ? row[i] : 0.0f;
         }
     }
 }
