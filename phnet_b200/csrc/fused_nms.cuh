@@ -49,6 +49,7 @@ struct FusedParams {
     float thr;
     FusedLayout L;
     const int *topm;   // optional [F, kTopM] candidate slots (header + row) of the best-ranked proposals (phnms_topm_kernel)
+    int topm_count;    // candidate slots per frame in `topm` (<= kTopM)
     long long *trace;  // optional: CTA 0 / thread 0 writes clock64() at phase boundaries (phnms_forward_f32_trace)
     int trace_len;
 };

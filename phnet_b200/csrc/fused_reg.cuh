@@ -22,7 +22,8 @@
 namespace phnms {
 
 constexpr int kCand = 4;   // candidates every CTA publishes per exchange (fallback batches)
-constexpr int kTopM = 8;   // per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch)
+constexpr int kTopM = 16;  // capacity: per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch);
+                           // FusedParams::topm_count (8 for top_k <= 4, else 16) of them are produced and fetched
 constexpr int kHdr = 32;   // candidate header bytes: {key, index, start, end, mask0, mask1, mask2, aux}
 
 // A candidate slot = 32-byte header + the proposal's row padded to a multiple of 4 words.
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
     uint32_t load_phase = 0, round_ctr = 0, fpar = 0;
     int tcount = 0;
     (void)tcount;
-    if (cl < p.F) request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(kTopM * SLOT), sbuf);
+    if (cl < p.F) request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(p.topm_count * SLOT), sbuf);
     // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
     // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
     const int lcap = min(T * CPT - p.rpc, 31);
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         // ---- request the next frame now; it lands while this frame's rounds run ----------------------------------
         if (f + ncl < p.F)
             request_slab(p, f + ncl, rank, rows_buf, bar_load, tid, T, P,
-                         pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(kTopM * SLOT),
+                         pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(p.topm_count * SLOT),
                          sbuf + (fpar ^ 1u) * sbuf_stride);
         PHNMS_TRACE(4);  // next slab requested
 

@@ -70,26 +70,37 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
         const bool reg_ok = (n_off == 36 || n_off == 72) && t.variant != PHNMS_FUSED_SMEM;
         if (reg_ok) {
             const int max_cpt = (n_off == 36) ? 2 : 1;
+            // A CTA wants >= 8 "spare lanes" beyond its rows: they hold the batch's candidates (fused_reg.cuh), without
+            // them every round after the first costs a cluster exchange.  Prefer the smallest cluster that leaves room.
+            const int kSpare = 8;
             int csize = 0;
-            for (int i = 0; i < 5 && !csize; ++i) {
-                const int c = cand[i];
-                if (t.cluster && c != t.cluster) continue;
-                const int rpc = rows_for(c);
-                if (rpc > 512 * max_cpt) continue;
-                if (freg_layout(rpc, P, c).total > smem_max) continue;
-                csize = c;
+            for (int pass = 0; pass < 2 && !csize; ++pass) {
+                const int need = pass == 0 ? kSpare : 0;
+                for (int i = 0; i < 5 && !csize; ++i) {
+                    const int c = cand[i];
+                    if (t.cluster && c != t.cluster) continue;
+                    const int rpc = rows_for(c);
+                    if (rpc + need > 512 * max_cpt) continue;
+                    if (freg_layout(rpc, P, c).total > smem_max) continue;
+                    csize = c;
+                }
             }
             if (csize) {
                 const int rpc = rows_for(csize);
-                int threads = t.threads ? t.threads : round_up(rpc, 32);
-                if (threads > 512) threads = 512;
-                if (threads < 128) threads = 128;
-                if (threads % 32) return PHNMS_ERR_TUNING;
-                int cpt = (rpc + threads - 1) / threads;
-                if (cpt > max_cpt) {
-                    if (t.threads) return PHNMS_ERR_TUNING;
-                    threads = 512;
+                int threads, cpt;
+                if (t.threads) {
+                    threads = t.threads;
+                    if (threads > 512 || threads < 128 || threads % 32) return PHNMS_ERR_TUNING;
                     cpt = (rpc + threads - 1) / threads;
+                    if (cpt > max_cpt) return PHNMS_ERR_TUNING;
+                } else {
+                    // two proposals per thread where the registers allow it (n_off 36): better ILP, shared `a` loads
+                    cpt = max_cpt;
+                    threads = round_up((rpc + kSpare + cpt - 1) / cpt, 32);
+                    if (threads > 512) threads = 512;
+                    if (threads < 128) threads = 128;
+                    if (threads * cpt < rpc) return PHNMS_ERR_TUNING;
+                    if (threads >= rpc + kSpare) cpt = 1;
                 }
                 const FregLayout L = freg_layout(rpc, P, csize);
                 int per_sm = smem_max / (L.total + 1024);
@@ -110,7 +121,7 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
                 pl->smem_bytes = L.total;
                 pl->grid = (int)(clusters * csize);
                 pl->launches = 2;  // phnms_topm_kernel + phnms_freg_kernel
-                pl->workspace_bytes = (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 256;   // candidate block per frame
+                pl->workspace_bytes = (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 256;   // candidate block per frame (capacity)
                 return PHNMS_OK;
             }
             if (t.variant == PHNMS_FUSED_REG) return PHNMS_ERR_TUNING;
@@ -364,9 +375,13 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
         fp.trace = reinterpret_cast<long long *>(trace);
         fp.trace_len = trace_len;
         fp.topm = nullptr;
+        fp.topm_count = 0;
         if (pl.variant == PHNMS_FUSED_REG) {
             if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
             int *topm = reinterpret_cast<int *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+            // enough candidates that the first batch usually reaches top_k without an exchange
+            const int topm_count = (top_k > 0 && top_k <= 4) ? 8 : kTopM;
+            fp.topm_count = topm_count;
             {
                 int warps = kTopmWarps;
                 while (warps > 1 && topm_smem_bytes((int)N, warps) > 160 * 1024) warps >>= 1;
@@ -376,7 +391,7 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                     if (e2 != cudaSuccess) return (int)e2;
                 }
                 phnms_topm_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(
-                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm);
+                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, topm);
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;

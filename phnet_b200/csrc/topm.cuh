@@ -21,7 +21,7 @@ inline size_t topm_smem_bytes(int N, int warps) { return (size_t)warps * 32 * ((
 __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float *__restrict__ props,
                                                                     const float *__restrict__ scores,
                                                                     const int32_t *__restrict__ n_valid, long long F,
-                                                                    int N, int n_off, int sort_model,
+                                                                    int N, int n_off, int sort_model, int count,
                                                                     int *__restrict__ topm) {
     extern __shared__ __align__(16) unsigned char smem_topm[];
     __shared__ float bit_key[kTopmWarps][32];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
             }
         }
         __syncwarp();
-        for (int j = 0; j < kTopM; ++j) {
+        for (int j = 0; j < count; ++j) {
             const u64 best = warp_min_u64(gmin);
             if (best == kNone64) break;
             if (lane == j) mine = best;
@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
     // padded to a multiple of 4 words -- byte for byte what the fused kernel keeps in shared memory, so that it can pull
     // the whole block with one bulk copy.  aux of slot 0 = number of valid candidates.
     const int P = 5 + n_off, P4 = (P + 3) & ~3, slot_words = 8 + P4;
-    int *blk = topm + (size_t)f * kTopM * slot_words;
-    const bool ok = lane < kTopM && mine != kNone64;
-    const int count = __popc(__ballot_sync(0xffffffffu, ok));
-    if (lane < kTopM) {
-        uint4 h0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), h1 = make_uint4(0u, 0u, 0u, (uint32_t)count);
+    int *blk = topm + (size_t)f * count * slot_words;
+    const bool ok = lane < count && mine != kNone64;
+    const int nfound = __popc(__ballot_sync(0xffffffffu, ok));
+    if (lane < count) {
+        uint4 h0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), h1 = make_uint4(0u, 0u, 0u, (uint32_t)nfound);
         if (ok) {
             const uint32_t idx = (uint32_t)mine;
             const float *row = props + ((size_t)f * N + idx) * P;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
             uint32_t m[3];
             range_mask<3>(st, en, m);
             h0 = make_uint4((uint32_t)(mine >> 32), idx, (uint32_t)st, (uint32_t)en);
-            h1 = make_uint4(m[0], m[1], m[2], (uint32_t)count);
+            h1 = make_uint4(m[0], m[1], m[2], (uint32_t)nfound);
         }
         uint4 *out = reinterpret_cast<uint4 *>(blk + (size_t)lane * slot_words);
         out[0] = h0;
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
         float rv[kTopM][3];
 #pragma unroll
         for (int j = 0; j < kTopM; ++j) {
+            if (j >= count) break;
             const u64 kj = __shfl_sync(0xffffffffu, mine, j);
             const float *row = props + ((size_t)f * N + (kj == kNone64 ? 0u : (uint32_t)kj)) * P;
 #pragma unroll
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
         }
 #pragma unroll
         for (int j = 0; j < kTopM; ++j) {
+            if (j >= count) break;
             float *dst = reinterpret_cast<float *>(blk + (size_t)j * slot_words + 8);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
             }
         }
     } else {
-        for (int j = 0; j < kTopM; ++j) {
+        for (int j = 0; j < count; ++j) {
             const u64 kj = __shfl_sync(0xffffffffu, mine, j);
             float *dst = reinterpret_cast<float *>(blk + (size_t)j * slot_words + 8);
             const float *row = props + ((size_t)f * N + (kj == kNone64 ? 0u : (uint32_t)kj)) * P;

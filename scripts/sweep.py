@@ -22,7 +22,7 @@ def main():
     bpf = N * (4 * n_off + 40) + 8
     res = []
     variants = [int(v) for v in os.environ.get('VARIANTS', '2,1').split(',')]
-    combos = [(v, c, t, 0) for v in variants for c in (1, 2, 4, 8) for t in (128, 256, 512)]
+    combos = [(v, c, t, 0) for v in variants for c in (1, 2, 4, 8) for t in (128, 256, 384, 512)]
     for v, c, t, m in combos:
         try:
             tune = _capi.tuning(path=1, cluster=c, threads=t, max_clusters=m, variant=v)
