@@ -119,6 +119,25 @@ size_t phnms_order_workspace_bytes(int64_t F, int64_t N);
 int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int sort_model,
                     int64_t *order, void *ws, size_t ws_bytes, void *stream);
 
+/*
+ * get_lanes for a whole clip (the callers either side of the op): libs/models/Router4OL.py:447-470 and
+ * RouterV4.py:404-428 for T frames in 4 launches and no host sync.
+ *
+ *   pred       [T, A, hdr + n_off] fp32 device: raw head output per prior: (logit0, logit1, start_y, start_x, theta, length,
+ *              [invalid_length when hdr == 7], x_0 .. x_{n_off-1}), x and start_x normalised to [0, 1]
+ *   hdr        6 (OpenLane-V models) or 7 (VIL-100 models)
+ *   score = softmax(logits)[1]; priors with score >= conf_threshold survive, in prior order; the NMS rows are
+ *   (logit0, logit1, start_y, start_x * (img_w-1), length * (n_off-1), x * (img_w-1)); overlap = nms_thres; top_k = max_lanes
+ *   out_rows   [T, top_k, hdr + n_off]: pred[kept] with columns 5 .. hdr-1 replaced by round(col * (n_off-1)), zero padded
+ *   out_num    [T] int64 lanes kept;  out_index [T, top_k] int64 kept priors' indices in the unfiltered frame
+ *   keep_inds  [T, A] uint8: the confidence mask (`keep_inds` of the reference)
+ */
+size_t phnms_get_lanes_workspace_bytes(int64_t T, int64_t A, int n_off, const phnms_tuning *tuning /* nullable */);
+int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int hdr, float conf_threshold, float img_w,
+                        float nms_thres, int64_t top_k, int sort_model, float *out_rows, int64_t *out_num,
+                        int64_t *out_index, unsigned char *keep_inds, void *ws, size_t ws_bytes,
+                        const phnms_tuning *tuning /* nullable */, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
 EXPORTS = (
     "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query",
     "phnms_forward_f32", "phnms_forward_f32_trace", "phnms_order_workspace_bytes", "phnms_order_f32",
+    "phnms_get_lanes_workspace_bytes", "phnms_get_lanes_f32",
 )
 
 
@@ -65,6 +66,11 @@ def lib() -> ctypes.CDLL:
     L.phnms_forward_f32.restype = ci
     L.phnms_forward_f32_trace.argtypes = L.phnms_forward_f32.argtypes + [vp, ci]
     L.phnms_forward_f32_trace.restype = ci
+    L.phnms_get_lanes_workspace_bytes.argtypes = [i64, i64, ci, ctypes.POINTER(Tuning)]
+    L.phnms_get_lanes_workspace_bytes.restype = sz
+    L.phnms_get_lanes_f32.argtypes = [vp, i64, i64, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, i64, ci,
+                                      vp, vp, vp, vp, vp, sz, ctypes.POINTER(Tuning), vp]
+    L.phnms_get_lanes_f32.restype = ci
     L.phnms_order_workspace_bytes.argtypes = [i64, i64]
     L.phnms_order_workspace_bytes.restype = sz
     L.phnms_order_f32.argtypes = [vp, vp, i64, i64, ci, vp, vp, sz, vp]

@@ -12,6 +12,7 @@
 #include "fused_reg.cuh"
 #include "tiled_nms.cuh"
 #include "topm.cuh"
+#include "frontend.cuh"
 
 using namespace phnms;
 
@@ -438,6 +439,52 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                                                       reinterpret_cast<long long *>(keep),
                                                       reinterpret_cast<long long *>(num_keep),
                                                       reinterpret_cast<long long *>(parent));
+    return (int)cudaGetLastError();
+}
+
+// ---- get_lanes for a clip: prepare -> lane NMS -> gather -----------------------------------------------------------------
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t phnms_get_lanes_workspace_bytes(int64_t T, int64_t A, int n_off, const phnms_tuning *tuning) {
+    if (T < 0 || A < 0 || check_shape(T, A, n_off) != PHNMS_OK) return 0;
+    const size_t P = 5 + (size_t)n_off;
+    return 256 + align256((size_t)T * A * P * 4) + align256((size_t)T * A * 4) * 2 + align256((size_t)T * 4) +
+           align256((size_t)T * A * 8) * 2 + align256((size_t)T * 8) + align256(phnms_workspace_bytes(T, A, n_off, tuning));
+}
+
+int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int hdr, float conf_threshold, float img_w,
+                        float nms_thres, int64_t top_k, int sort_model, float *out_rows, int64_t *out_num,
+                        int64_t *out_index, unsigned char *keep_inds, void *ws, size_t ws_bytes,
+                        const phnms_tuning *tuning, void *stream_) {
+    int rc = check_shape(T, A, n_off);
+    if (rc != PHNMS_OK) return rc;
+    if ((hdr != 6 && hdr != 7) || top_k < 1 || top_k > A) return PHNMS_ERR_BAD_ARG;
+    if (T == 0 || A == 0) return PHNMS_OK;
+    if (!pred || !out_rows || !out_num || !out_index || !keep_inds) return PHNMS_ERR_BAD_ARG;
+    if (!ws || ws_bytes < phnms_get_lanes_workspace_bytes(T, A, n_off, tuning)) return PHNMS_ERR_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t P = 5 + (size_t)n_off;
+    unsigned char *b = reinterpret_cast<unsigned char *>(align256((size_t)ws));
+    float *cprops = reinterpret_cast<float *>(b);            b += align256((size_t)T * A * P * 4);
+    float *cscores = reinterpret_cast<float *>(b);           b += align256((size_t)T * A * 4);
+    int *src = reinterpret_cast<int *>(b);                   b += align256((size_t)T * A * 4);
+    int *n_valid = reinterpret_cast<int *>(b);               b += align256((size_t)T * 4);
+    int64_t *keep = reinterpret_cast<int64_t *>(b);          b += align256((size_t)T * A * 8);
+    int64_t *parent = reinterpret_cast<int64_t *>(b);        b += align256((size_t)T * A * 8);
+    unsigned char *nms_ws = b;
+    const size_t nms_ws_bytes = phnms_workspace_bytes(T, A, n_off, tuning);
+    const float n_strips = (float)(n_off - 1);
+    phnms_prepare_kernel<<<(unsigned)T, kPrepThreads, (size_t)A * sizeof(int), stream>>>(
+        pred, (int)A, hdr, n_off, conf_threshold, img_w - 1.0f, n_strips, cprops, cscores, src, n_valid, keep_inds);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    rc = phnms_forward_f32(cprops, cscores, n_valid, T, A, n_off, nms_thres, top_k, sort_model, keep, out_num, parent,
+                           nms_ws_bytes ? nms_ws : nullptr, nms_ws_bytes, tuning, stream_);
+    if (rc != PHNMS_OK) return rc;
+    phnms_gather_kernel<<<(unsigned)T, 128, 0, stream>>>(pred, (int)A, hdr, n_off, n_strips,
+                                                       reinterpret_cast<const long long *>(keep),
+                                                       reinterpret_cast<const long long *>(out_num), src, (int)top_k,
+                                                       out_rows, reinterpret_cast<long long *>(out_index));
     return (int)cudaGetLastError();
 }
 
