@@ -88,6 +88,19 @@ __device__ __forceinline__ bool warp_pair_hit(const float *a, const float *b, bo
     return act && (dist < __fmul_rn(thr, (float)len));  // :46
 }
 
+// One pair, one thread (used where only a handful of pairs is needed, e.g. candidate-vs-candidate in topm.cuh).
+// sb/eb and sa/ea are the lanes' own bounds with the ends already clamped to n_off-1.
+__device__ __forceinline__ bool pair_hit_scalar(const float *a, const float *b, int sa, int ea, int sb, int eb, float thr) {
+    const int start = max(sa, sb), end = min(ea, eb);              // nms_kernel.cu:31,34
+    if (end < start) return false;                                  // :36
+    const int i0 = (int)(((uint32_t)start + 5u) & 255u);            // :38 unsigned char counter
+    const int last = (int)((uint32_t)end + 5u);
+    float dist = 0.0f;
+    for (int i = i0; i <= last; ++i) dist = __fadd_rn(dist, fabsf(__fsub_rn(a[i], b[i])));
+    const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
+    return dist < __fmul_rn(thr, (float)len);                       // :46
+}
+
 // ---- warp helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
     const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;

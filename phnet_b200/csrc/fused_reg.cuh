@@ -24,6 +24,7 @@ namespace phnms {
 constexpr int kCand = 4;   // candidates every CTA publishes per exchange (fallback batches)
 constexpr int kTopM = 16;  // capacity: per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch);
                            // FusedParams::topm_count (8 for top_k <= 4, else 16) of them are produced and fetched
+constexpr bool kDualPass = false;  // evaluate two kept lanes per pass (more ILP, but measured slower: predicate pressure)
 constexpr int kHdr = 32;   // candidate header bytes: {key, index, start, end, mask0, mask1, mask2, aux}
 
 // A candidate slot = 32-byte header + the proposal's row padded to a multiple of 4 words.
@@ -173,6 +174,104 @@ __device__ __forceinline__ void request_slab(const FusedParams &p, long long f, 
     }
 }
 
+// devIoU of NK kept lanes (headers hdr[k] in shared memory, rows 32 bytes behind them) against this thread's lanes, in
+// ONE pass over the registers: NK independent fp32 chains, each the reference's ascending sequential sum (:38-44).
+// A lane's in-range bitmask for a pair is the AND of the two per-lane masks ([max(sa,sb), min(ea,eb)] is the
+// intersection of the two ranges) -- unless BOTH starts are below -5, where the reference's unsigned-char counter wraps
+// (rare; recomputed from the wrapped counter).  A start in [-5,-1] pulls header words 0..4 into the sum; they are not in
+// registers and are re-read (rare).  parent is stamped in keep order, so the last kept lane that covers a lane wins.
+template <int NOFF, int CPT, int NK, typename HdrFn>
+__device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, const unsigned char *const (&hdr)[NK],
+                                          const bool (&live)[CPT], const u64 (&myK)[CPT], const int (&st)[CPT],
+                                          const int (&en)[CPT], const uint32_t (&mb)[CPT][(5 + NOFF + 31) / 32],
+                                          const float (&x)[CPT][NOFF], HdrFn my_hdr,
+                                          uint32_t (&par)[CPT], bool (&hit_out)[NK][CPT], long long n_base) {
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3;
+    u64 wk[NK];
+    uint32_t a_addr[NK];
+    uint32_t m[NK][CPT][MW];
+    float dist[NK][CPT];
+    bool act[NK][CPT];
+    int len[NK][CPT];
+    bool any_act = false, hdr_terms = false;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const uint4 wh = *reinterpret_cast<const uint4 *>(hdr[k]);
+        const uint4 wm = *reinterpret_cast<const uint4 *>(hdr[k] + 16);
+        wk[k] = ((u64)wh.x << 32) | wh.y;
+        const int sa = (int)wh.z, ea = (int)wh.w;
+        const uint32_t ma[3] = {wm.x, wm.y, wm.z};
+        a_addr[k] = smem_u32(hdr[k] + kHdr);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int start = max(sa, st[c]);   // nms_kernel.cu:31
+            const int end = min(ea, en[c]);     // :34 (both clamped to NOFF-1)
+            act[k][c] = live[c] && (myK[c] > wk[k]) && (end >= start);  // :36
+            len[k][c] = (int)((uint32_t)end - (uint32_t)start + 1u);
+#pragma unroll
+            for (int w = 0; w < MW; ++w) m[k][c][w] = act[k][c] ? (ma[w] & mb[c][w]) : 0u;
+            if (act[k][c] && start < -5) {      // :38 unsigned char counter wrapped: (5 + start) & 255
+                const int i0 = (int)(((uint32_t)start + 5u) & 255u), last = (int)((uint32_t)end + 5u);
+                const bool run = i0 <= last;    // then 0 <= last <= NOFF+4: nothing below can wrap
+#pragma unroll
+                for (int w = 0; w < MW; ++w) {
+                    const int l = max(i0 - 32 * w, 0), hh = min((run ? last : -1) - 32 * w, 31);
+                    m[k][c][w] = (run && l <= hh) ? ((0xffffffffu >> (31 - hh)) & (0xffffffffu << l)) : 0u;
+                }
+            }
+            dist[k][c] = 0.0f;
+            any_act |= act[k][c];
+            hdr_terms |= (m[k][c][0] & 0x1fu) != 0u;
+        }
+    }
+    if (__any_sync(0xffffffffu, any_act)) {
+        if (__any_sync(0xffffffffu, hdr_terms)) {
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const float *arow = reinterpret_cast<const float *>(hdr[k] + kHdr);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c)
+                    if (m[k][c][0] & 0x1fu) {
+                        const float *mine = my_hdr(c);
+                        for (int i = 0; i < 5; ++i)
+                            if (m[k][c][0] & (1u << i))
+                                dist[k][c] = __fadd_rn(dist[k][c], fabsf(__fsub_rn(arow[i], mine[i])));
+                    }
+            }
+        }
+#pragma unroll
+        for (int g = 1; g < P4 / 4; ++g) {
+            float a4[NK][4];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const float4 av = lds_v4(a_addr[k] + 16 * g);
+                a4[k][0] = av.x; a4[k][1] = av.y; a4[k][2] = av.z; a4[k][3] = av.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = 4 * g + u;
+                if (i >= 5 && i < P) {
+#pragma unroll
+                    for (int k = 0; k < NK; ++k)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            const float t = __fsub_rn(a4[k][u], x[c][i - 5]);
+                            if (m[k][c][i >> 5] & (1u << (i & 31))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t));
+                        }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const bool hit = act[k][c] && (dist[k][c] < __fmul_rn(p.thr, (float)len[k][c]));  // :46
+            hit_out[k][c] = hit;
+            if (hit || myK[c] == wk[k]) par[c] = (uint32_t)(n_base + k + 1);                  // :127,:129
+        }
+}
+
 #define PHNMS_TRACE(tag)                                                                      \
     do {                                                                                      \
         if (kTrace && p.trace && p.trace_len > 0 && blockIdx.x == 0 && tid == 0 && tcount + 1 < p.trace_len) { \
@@ -315,22 +414,66 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         // last published one) and that guaranteed prefix is consumed with no further communication.
         long long n = 0;
         bool frame_done = false;
-        bool first_batch = p.topm != nullptr;
+
+        // ---- batch 0, planned: the candidate block carries, for every candidate, which later candidates it suppresses
+        // (computed by phnms_topm_kernel).  The greedy scan over the candidates is therefore known before a single
+        // column is touched: no selection, no exchange, no barrier -- the kept candidates are evaluated two per pass.
+        if (p.topm != nullptr) {
+            const unsigned char *csl = pslots + (size_t)fpar * kTopM * L.slot_stride;
+            const uint32_t aux = lane < kTopM ? reinterpret_cast<const uint32_t *>(csl + (size_t)lane * L.slot_stride)[7] : 0u;
+            const int nc = min((int)(__shfl_sync(0xffffffffu, aux, 0) & 0xffffu), p.topm_count);
+            uint32_t alive = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u), kept = 0u;
+            long long nk = 0;
+            for (int i = 0; i < nc; ++i) {
+                const uint32_t adj = __shfl_sync(0xffffffffu, aux, i) >> 16;
+                if ((alive >> i) & 1u) {
+                    kept |= 1u << i;
+                    alive &= ~adj;
+                    ++nk;
+                    if (nk == p.top_k) break;   // nms_kernel.cu:133
+                }
+            }
+            auto real_hdr = [&](int c) { return p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P; };
+            while (kept) {
+                const int i0 = __ffs(kept) - 1;
+                kept &= kept - 1u;
+                const int i1 = (kDualPass && kept) ? __ffs(kept) - 1 : -1;   // second lane of this pass (if dual passes are on)
+                if (i1 >= 0) kept &= kept - 1u;
+                const unsigned char *h0 = csl + (size_t)i0 * L.slot_stride;
+                if (rank == 0 && tid == 0) {                                                       // :118
+                    p.keep[(size_t)f * p.N + n] = (long long)reinterpret_cast<const uint32_t *>(h0)[1];
+                    if (i1 >= 0)
+                        p.keep[(size_t)f * p.N + n + 1] =
+                            (long long)reinterpret_cast<const uint32_t *>(csl + (size_t)i1 * L.slot_stride)[1];
+                }
+                if (i1 >= 0) {
+                    const unsigned char *const hh[2] = {h0, csl + (size_t)i1 * L.slot_stride};
+                    bool hit[2][CPT];
+                    freg_eval<NOFF, CPT, 2>(p, f, hh, real, myK, st, en, mb, x, real_hdr, par, hit, n);
+                    n += 2;
+                } else {
+                    const unsigned char *const hh[1] = {h0};
+                    bool hit[1][CPT];
+                    freg_eval<NOFF, CPT, 1>(p, f, hh, real, myK, st, en, mb, x, real_hdr, par, hit, n);
+                    n += 1;
+                }
+            }
+            PHNMS_TRACE(11);  // planned batch done
+            // done when top_k lanes are kept, or when every lane of the frame was a candidate
+            if (n == p.top_k || nc >= nv) frame_done = true;
+        }
+
+        // ---- fallback batches (needed when the candidates run out before top_k lanes are kept): every CTA publishes its
+        // best kCand alive lanes; the merged list is exact up to the smallest "last published key" (an unpublished alive
+        // lane of CTA d ranks after d's last published one) and that guaranteed prefix is consumed with no further
+        // communication -- spare lanes hold register copies of the candidates and flag the ones a winner suppresses.
         while (!frame_done) {
             const unsigned char *hb;   // headers of this batch in rank order
             int hs;                    // header stride
             const unsigned char *sl;   // slots that hold the rows
             uint32_t dead_row;
             int lcount;
-            const bool fb = first_batch;
-            if (first_batch) {
-                first_batch = false;
-                sl = pslots + (size_t)fpar * kTopM * L.slot_stride;
-                hb = sl;
-                hs = L.slot_stride;
-                dead_row = 2u;
-                lcount = min((int)reinterpret_cast<const uint32_t *>(sl)[7], 1 + lcap);
-            } else {
+            {
                 const uint32_t par_bit = round_ctr & 1u, xphase = (round_ctr >> 1) & 1u;
                 ++round_ctr;
                 dead_row = par_bit;
@@ -506,7 +649,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
                         mb[c][0] = h1.x;
                         if (MW > 1) mb[c][MW > 1 ? 1 : 0] = h1.y;
                         if (MW > 2) mb[c][MW > 2 ? 2 : 0] = h1.z;
-                        const float *row = reinterpret_cast<const float *>(sl + (size_t)(fb ? 1 + v : (int)h1.w) * L.slot_stride + kHdr);
+                        const float *row = reinterpret_cast<const float *>(sl + (size_t)h1.w * L.slot_stride + kHdr);
 #pragma unroll
                         for (int i = 0; i < NOFF; ++i) x[c][i] = row[5 + i];
                         par[c] = 0u;
@@ -516,106 +659,36 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             PHNMS_TRACE(10);  // spare lanes loaded
 
             // 6. one round per alive candidate of the prefix, in rank order
+            auto any_hdr = [&](int c) -> const float * {
+                if (real[c]) return p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P;
+                const int v = c * T + tid - p.rpc;
+                return reinterpret_cast<const float *>(
+                    sl + (size_t)reinterpret_cast<const uint32_t *>(hb + (size_t)(1 + v) * hs)[7] * L.slot_stride + kHdr);
+            };
+            bool live[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) live[c] = real[c] || virt[c];
             for (int j = 0; j < lcount; ++j) {
                 if (j > 0 && cdead[dead_row * 32 + j] != 0u) continue;  // suppressed by an earlier winner of this batch
                 const unsigned char *h = hb + (size_t)j * hs;
-                const uint4 wh = *reinterpret_cast<const uint4 *>(h);
-                const uint4 wm = *reinterpret_cast<const uint4 *>(h + 16);
-                const u64 wk = ((u64)wh.x << 32) | wh.y;
-                const int sa = (int)wh.z, ea = (int)wh.w;
-                const unsigned char *arow_b = sl + (size_t)(fb ? j : (int)wm.w) * L.slot_stride + kHdr;
-                const uint32_t a_addr = smem_u32(arow_b);
-                if (rank == 0 && tid == 0) p.keep[(size_t)f * p.N + n] = (long long)(uint32_t)wk;  // :118
-
-                // devIoU(kept lane, my lanes): in-range bitmask per lane, fully unrolled ascending sum (:38-44).
-                // [max(sa,sb), min(ea,eb)] is the intersection of the two lanes' own ranges, so the pair's bitmask is
-                // the AND of the two per-lane bitmasks (both precomputed) -- unless BOTH starts are below -5, where the
-                // reference's unsigned-char counter wraps (rare; recomputed from the wrapped counter).
-                const uint32_t ma[3] = {wm.x, wm.y, wm.z};
-                uint32_t m[CPT][MW];
-                float dist[CPT];
-                bool act[CPT];
-                int len[CPT];
-                bool any_act = false;
+                // the compact header points at the slot that holds the row: build {header, row} view of that slot
+                const unsigned char *slot = sl + (size_t)reinterpret_cast<const uint32_t *>(h)[7] * L.slot_stride;
+                if (rank == 0 && tid == 0) p.keep[(size_t)f * p.N + n] = (long long)reinterpret_cast<const uint32_t *>(h)[1];
+                const unsigned char *const hh[1] = {slot};
+                bool hit[1][CPT];
+                freg_eval<NOFF, CPT, 1>(p, f, hh, live, myK, st, en, mb, x, any_hdr, par, hit, n);
+                // A suppressed candidate is flagged for the LATER round that would have picked it (read after at least
+                // one barrier).  The winner's own copy must not touch its flag: slower warps may not have read it yet at
+                // the top of THIS round (that race skipped the round in some warps -> hang).
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int start = max(sa, st[c]);   // :31
-                    const int end = min(ea, en[c]);     // :34 (both clamped to NOFF-1)
-                    act[c] = (real[c] || virt[c]) && (myK[c] > wk) && (end >= start);  // :36
-                    len[c] = (int)((uint32_t)end - (uint32_t)start + 1u);
-#pragma unroll
-                    for (int w = 0; w < MW; ++w) m[c][w] = act[c] ? (ma[w] & mb[c][w]) : 0u;
-                    if (act[c] && start < -5) {            // :38 unsigned char counter wrapped: (5 + start) & 255
-                        const int i0 = (int)(((uint32_t)start + 5u) & 255u), last = (int)((uint32_t)end + 5u);
-                        const bool run = i0 <= last;       // then 0 <= last <= NOFF+4: nothing below can wrap
-#pragma unroll
-                        for (int w = 0; w < MW; ++w) {
-                            const int l = max(i0 - 32 * w, 0), hh = min((run ? last : -1) - 32 * w, 31);
-                            m[c][w] = (run && l <= hh) ? ((0xffffffffu >> (31 - hh)) & (0xffffffffu << l)) : 0u;
-                        }
-                    }
-                    dist[c] = 0.0f;
-                    any_act |= act[c];
-                }
-                PHNMS_TRACE(14);  // round set-up
-                if (__any_sync(0xffffffffu, any_act)) {
-                    // rare: a start in [-5,-1] pulls header columns 0..4 into the sum (:38); they come first
-                    bool hdr_terms = false;
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) hdr_terms |= (m[c][0] & 0x1fu) != 0u;
-                    if (__any_sync(0xffffffffu, hdr_terms)) {
-                        const float *arow = reinterpret_cast<const float *>(arow_b);
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) {
-                            if (m[c][0] & 0x1fu) {
-                                const int v = c * T + tid - p.rpc;
-                                const float *mine_hdr;
-                                if (real[c]) {
-                                    mine_hdr = p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P;
-                                } else {
-                                    const int sidx = fb ? 1 + v : (int)reinterpret_cast<const uint32_t *>(hb + (size_t)(1 + v) * hs)[7];
-                                    mine_hdr = reinterpret_cast<const float *>(sl + (size_t)sidx * L.slot_stride + kHdr);
-                                }
-                                for (int i = 0; i < 5; ++i)
-                                    if (m[c][0] & (1u << i)) dist[c] = __fadd_rn(dist[c], fabsf(__fsub_rn(arow[i], mine_hdr[i])));
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int g = 1; g < P4 / 4; ++g) {
-                        const float4 av = lds_v4(a_addr + 16 * g);
-                        const float a4[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = 4 * g + u;
-                            if (i >= 5 && i < P) {
-#pragma unroll
-                                for (int c = 0; c < CPT; ++c) {
-                                    const float t = __fsub_rn(a4[u], x[c][i - 5]);
-                                    if (m[c][i >> 5] & (1u << (i & 31))) dist[c] = __fadd_rn(dist[c], fabsf(t));
-                                }
-                            }
-                        }
-                    }
-                }
-                PHNMS_TRACE(15);  // offset loop
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const bool hit = act[c] && (dist[c] < __fmul_rn(p.thr, (float)len[c]));  // :46
-                    if (hit || myK[c] == wk) par[c] = (uint32_t)(n + 1);                      // :127,:129
-                    // A suppressed candidate is flagged for the LATER round that would have picked it (read after at
-                    // least one barrier).  The winner's own copy must not touch its flag: slower warps may not have
-                    // read it yet at the top of THIS round (that race skipped the round in some warps -> hang).
-                    if (virt[c] && hit) cdead[dead_row * 32 + 1 + (c * T + tid - p.rpc)] = 1u;
-                }
+                for (int c = 0; c < CPT; ++c)
+                    if (virt[c] && hit[0][c]) cdead[dead_row * 32 + 1 + (c * T + tid - p.rpc)] = 1u;
                 ++n;
-                PHNMS_TRACE(11);  // round done
                 if (n == p.top_k) {  // :133 (top_k == 0 never stops early)
                     frame_done = true;
                     break;
                 }
                 __syncthreads();  // candidate-dead flags of this round are visible to the next
-                PHNMS_TRACE(12);  // round barrier
             }
         }
 

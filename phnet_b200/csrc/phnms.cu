@@ -392,7 +392,7 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                     if (e2 != cudaSuccess) return (int)e2;
                 }
                 phnms_topm_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(
-                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, topm);
+                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, thresh, topm);
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;

@@ -16,12 +16,17 @@ constexpr int kTopmWarps = 4;
 
 // dynamic shared memory: per warp 33 * ceil(N / 32) u32 keys, stored group-major ([i % 32][i / 32], row pitch G+1... see
 // kidx) so that both the owner lane's column walk and the warp's row walk of one group are bank-conflict free.
-inline size_t topm_smem_bytes(int N, int warps) { return (size_t)warps * 32 * (((N + 31) / 32) | 1) * 4; }
+__host__ __device__ inline size_t topm_keys_bytes(int N, int warps) { return (size_t)warps * 32 * (((N + 31) / 32) | 1) * 4; }
+// + per warp: kTopM candidate rows (padded to 96 words), their bounds and one adjacency word each
+constexpr int kTopmRowWords = 96;
+inline size_t topm_smem_bytes(int N, int warps) {
+    return topm_keys_bytes(N, warps) + (size_t)warps * kTopM * (kTopmRowWords + 2 + 1) * 4;
+}
 
 __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float *__restrict__ props,
                                                                     const float *__restrict__ scores,
                                                                     const int32_t *__restrict__ n_valid, long long F,
-                                                                    int N, int n_off, int sort_model, int count,
+                                                                    int N, int n_off, int sort_model, int count, float thr,
                                                                     int *__restrict__ topm) {
     extern __shared__ __align__(16) unsigned char smem_topm[];
     __shared__ float bit_key[kTopmWarps][32];
@@ -123,21 +128,16 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
     int *blk = topm + (size_t)f * count * slot_words;
     const bool ok = lane < count && mine != kNone64;
     const int nfound = __popc(__ballot_sync(0xffffffffu, ok));
-    if (lane < count) {
-        uint4 h0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), h1 = make_uint4(0u, 0u, 0u, (uint32_t)nfound);
-        if (ok) {
-            const uint32_t idx = (uint32_t)mine;
-            const float *row = props + ((size_t)f * N + idx) * P;
-            const int st = lane_start(row[2], n_off);
-            const int en = lane_end(row[4], st, n_off);
-            uint32_t m[3];
-            range_mask<3>(st, en, m);
-            h0 = make_uint4((uint32_t)(mine >> 32), idx, (uint32_t)st, (uint32_t)en);
-            h1 = make_uint4(m[0], m[1], m[2], (uint32_t)nfound);
-        }
-        uint4 *out = reinterpret_cast<uint4 *>(blk + (size_t)lane * slot_words);
-        out[0] = h0;
-        out[1] = h1;
+    uint4 h0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), h1 = make_uint4(0u, 0u, 0u, (uint32_t)nfound);
+    if (ok) {
+        const uint32_t idx = (uint32_t)mine;
+        const float *row = props + ((size_t)f * N + idx) * P;
+        const int st = lane_start(row[2], n_off);
+        const int en = lane_end(row[4], st, n_off);
+        uint32_t m[3];
+        range_mask<3>(st, en, m);
+        h0 = make_uint4((uint32_t)(mine >> 32), idx, (uint32_t)st, (uint32_t)en);
+        h1 = make_uint4(m[0], m[1], m[2], (uint32_t)nfound);
     }
     // rows: the warp copies row j with coalesced loads and stores; all loads are issued before the first store
     if (P4 <= 96) {
@@ -153,6 +153,34 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
                 rv[j][t] = (kj != kNone64 && i < P) ? row[i] : 0.0f;
             }
         }
+        // candidate-vs-candidate predicate: bit j of adj[i] = devIoU(candidate i, candidate j), j ranked after i.  With it
+        // the fused kernel knows, before touching a single column, which candidates the greedy scan keeps.
+        float *crow = reinterpret_cast<float *>(smem_topm + topm_keys_bytes(N, blockDim.x >> 5)) +
+                      (size_t)warp * kTopM * (kTopmRowWords + 3);
+        int *cse = reinterpret_cast<int *>(crow + kTopM * kTopmRowWords);
+        uint32_t *adj = reinterpret_cast<uint32_t *>(cse + 2 * kTopM);
+#pragma unroll
+        for (int j = 0; j < kTopM; ++j) {
+            if (j >= count) break;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) crow[j * kTopmRowWords + lane + 32 * t] = rv[j][t];
+        }
+        if (lane < kTopM) {
+            cse[2 * lane] = (int)h0.z;
+            cse[2 * lane + 1] = (int)h0.w;
+            adj[lane] = 0u;
+        }
+        __syncwarp();
+        for (int pr = lane; pr < nfound * (nfound - 1) / 2; pr += 32) {
+            int i = 0, rem = pr;
+            while (rem >= nfound - 1 - i) { rem -= nfound - 1 - i; ++i; }
+            const int j = i + 1 + rem;
+            if (pair_hit_scalar(crow + i * kTopmRowWords, crow + j * kTopmRowWords, cse[2 * i], cse[2 * i + 1], cse[2 * j],
+                                cse[2 * j + 1], thr))
+                atomicOr(&adj[i], 1u << j);
+        }
+        __syncwarp();
+        if (lane < count) h1.w = (adj[lane] << 16) | (uint32_t)nfound;
 #pragma unroll
         for (int j = 0; j < kTopM; ++j) {
             if (j >= count) break;
@@ -170,6 +198,11 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
             const float *row = props + ((size_t)f * N + (kj == kNone64 ? 0u : (uint32_t)kj)) * P;
             for (int i = lane; i < P4; i += 32) dst[i] = (kj != kNone64 && i < P) ? row[i] : 0.0f;
         }
+    }
+    if (lane < count) {   // aux = (adjacency bits << 16) | number of valid candidates
+        uint4 *out = reinterpret_cast<uint4 *>(blk + (size_t)lane * slot_words);
+        out[0] = h0;
+        out[1] = h1;
     }
 }
 
