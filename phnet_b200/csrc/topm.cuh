@@ -18,7 +18,7 @@ constexpr int kTopmWarps = 4;
 // kidx) so that both the owner lane's column walk and the warp's row walk of one group are bank-conflict free.
 __host__ __device__ inline size_t topm_keys_bytes(int N, int warps) { return (size_t)warps * 32 * (((N + 31) / 32) | 1) * 4; }
 // + per warp: kTopM candidate rows (padded to 96 words), their bounds and one adjacency word each
-constexpr int kTopmRowWords = 96;
+constexpr int kTopmRowWords = 97;   // odd pitch: candidate rows start in different banks
 inline size_t topm_smem_bytes(int N, int warps) {
     return topm_keys_bytes(N, warps) + (size_t)warps * kTopM * (kTopmRowWords + 2 + 1) * 4;
 }
