@@ -55,6 +55,29 @@ def _check_inputs(boxes: torch.Tensor, scores: torch.Tensor, batched: bool):
     return boxes, scores
 
 
+_ws_bytes_cache: dict = {}     # (F, N, n_off, tuning key) -> workspace bytes (a pure function of the shape)
+_ws_cache: dict = {}           # (device index, stream handle) -> reusable workspace tensor for small calls
+
+
+def _workspace(L, dev, stream, F, N, n_off, t, tp):
+    key = (F, N, n_off, None if t is None else (t.path, t.cluster, t.threads, t.max_clusters, t.variant))
+    nbytes = _ws_bytes_cache.get(key)
+    if nbytes is None:
+        nbytes = _ws_bytes_cache[key] = int(L.phnms_workspace_bytes(F, N, n_off, tp))
+    if nbytes == 0:
+        return None, 0
+    if nbytes > (1 << 20):                      # large batches: a fresh allocation (stream-ordered by the caching allocator)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return ws, nbytes
+    # per-frame calls: one small workspace per (device, stream), reused -- launches on one stream are ordered
+    ck = (dev.index, stream)
+    ws = _ws_cache.get(ck)
+    if ws is None or ws.numel() < nbytes:
+        ws = _ws_cache[ck] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=dev)
+    return ws, nbytes
+
+
 def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tune, keep, num, parent):
     top_k = int(top_k)
     if top_k < 0:
@@ -62,16 +85,21 @@ def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tun
     L = _capi.lib()
     t = tune if isinstance(tune, _capi.Tuning) or tune is None else _capi.tuning(**tune)
     tp = ctypes.byref(t) if t is not None else None
-    ws_bytes = L.phnms_workspace_bytes(F, N, n_off, tp)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=boxes.device) if ws_bytes else None
-    with torch.cuda.device(boxes.device):
-        stream = torch.cuda.current_stream().cuda_stream
+    dev = boxes.device
+    switch = torch.cuda.current_device() != dev.index
+    if switch:
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev)
+    try:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, ws_bytes = _workspace(L, dev, stream, F, N, n_off, t, tp)
         rc = L.phnms_forward_f32(boxes.data_ptr(), scores.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
                                  F, N, n_off, float(overlap), top_k, int(sort_model), keep.data_ptr(), num.data_ptr(),
                                  parent.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, tp, stream)
+    finally:
+        if switch:
+            torch.cuda.set_device(prev)
     _capi.check(rc)
-    if ws is not None:
-        ws.record_stream(torch.cuda.current_stream(boxes.device))
 
 
 def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model: int = _capi.SORT_TORCH_CUDA,
@@ -83,10 +111,8 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model
     """
     boxes, scores = _check_inputs(boxes, scores, batched=False)
     N, P = boxes.shape
-    dev = boxes.device
-    keep = torch.empty(N, dtype=torch.int64, device=dev)
-    parent = torch.empty(N, dtype=torch.int64, device=dev)
-    num = torch.empty((), dtype=torch.int64, device=dev)
+    out = torch.empty(2 * N + 1, dtype=torch.int64, device=boxes.device)   # one allocation, three views
+    keep, parent, num = out[:N], out[N:2 * N], out[2 * N]
     _launch(boxes, scores, None, 1, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent)
     return [keep, num, parent]
 
