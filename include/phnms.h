@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PHNMS_ABI_VERSION 2
+#define PHNMS_ABI_VERSION 3
 
 #define PHNMS_OK 0
 #define PHNMS_ERR_BAD_ARG (-1)      /* null pointer, negative size, misaligned pointer                         */
@@ -53,12 +53,17 @@ extern "C" {
 #define PHNMS_FUSED_SMEM 1          /* proposals stay in shared memory; any n_off in [1, 250]                          */
 #define PHNMS_FUSED_REG 2           /* proposals held in registers, next frame's TMA load overlaps compute; n_off 36/72 */
 
+/* how frames are handed to the persistent clusters of the register-resident kernel */
+#define PHNMS_SCHED_STATIC 1        /* cluster c takes frames c, c + n_clusters, ...: fastest when the GPU is not shared         */
+#define PHNMS_SCHED_DYNAMIC 2       /* clusters claim frames from a counter: no second wave when another kernel holds some SMs   */
+
 typedef struct phnms_tuning {
     int path;            /* PHNMS_PATH_*                                             (0 = auto) */
     int cluster;         /* CTAs per frame for the fused path: 1,2,4,8,16            (0 = auto) */
     int threads;         /* threads per CTA for the fused path: multiple of 32, <=512 (0 = auto) */
     int max_clusters;    /* cap on resident clusters (persistent grid size)          (0 = auto) */
     int variant;         /* fused path: PHNMS_FUSED_SMEM or PHNMS_FUSED_REG          (0 = auto) */
+    int schedule;        /* register-resident kernel: PHNMS_SCHED_STATIC / _DYNAMIC   (0 = auto) */
 } phnms_tuning;
 
 typedef struct phnms_plan {

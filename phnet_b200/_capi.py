@@ -5,10 +5,11 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "csrc", "libphnms.so")
+SO_PATH = os.environ.get("PHNMS_SO") or os.path.join(HERE, "csrc", "libphnms.so")   # PHNMS_SO: A/B testing of builds
 
 PATH_AUTO, PATH_FUSED, PATH_TILED = 0, 1, 2
 FUSED_SMEM, FUSED_REG = 1, 2
+SCHED_STATIC, SCHED_DYNAMIC = 1, 2
 SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
 
 EXPORTS = (
@@ -20,7 +21,7 @@ EXPORTS = (
 
 class Tuning(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
-                ("max_clusters", ctypes.c_int), ("variant", ctypes.c_int)]
+                ("max_clusters", ctypes.c_int), ("variant", ctypes.c_int), ("schedule", ctypes.c_int)]
 
 
 class Plan(ctypes.Structure):
@@ -75,7 +76,7 @@ def lib() -> ctypes.CDLL:
     L.phnms_order_workspace_bytes.restype = sz
     L.phnms_order_f32.argtypes = [vp, vp, i64, i64, ci, vp, vp, sz, vp]
     L.phnms_order_f32.restype = ci
-    if L.phnms_abi_version() != 2:
+    if L.phnms_abi_version() != 3 and not os.environ.get("PHNMS_SO"):
         raise ImportError("libphnms.so ABI version mismatch; rebuild with `python -m phnet_b200.build`")
     _lib = L
     return L
@@ -86,10 +87,10 @@ def check(code: int) -> None:
         raise PhnmsError(code, lib().phnms_error_string(code).decode())
 
 
-def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0, variant: int = 0):
-    if not (path or cluster or threads or max_clusters or variant):
+def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0, variant: int = 0, schedule: int = 0):
+    if not (path or cluster or threads or max_clusters or variant or schedule):
         return None
-    return Tuning(path, cluster, threads, max_clusters, variant)
+    return Tuning(path, cluster, threads, max_clusters, variant, schedule)
 
 
 def plan(F: int, N: int, n_off: int, tune: Tuning | None = None) -> dict:

@@ -47,7 +47,7 @@ struct FregLayout {
 
 inline FregLayout freg_layout(int rpc, int P, int csize) {
     FregLayout L;
-    int o = 32;  // mbarriers: load @0, exchange @8 and @16
+    int o = 64;  // mbarriers: load @0, exchange @8 / @16, frame claim @24 / @32; claimed frame indices @40 / @48
     L.off_wtop = o;
     o += 2 * 32 * kCand * 8;
     L.off_bh = o;
@@ -87,6 +87,13 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_plain() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_async_b64(uint32_t dst, unsigned long long v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(v), "r"(bar)
+                 : "memory");
+}
 
 // Bits [5+start, 5+end] of one lane's own offset range (start below -5 acts as "no lower bound": the other lane's
 // start wins the max).  Bit i corresponds to row word i (columns 0..4 are the header, nms_kernel.cu:38).
@@ -280,7 +287,7 @@ __device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, con
         }                                                                                     \
     } while (0)
 
-template <int NOFF, int CPT, bool kTrace>
+template <int NOFF, int CPT, bool kTrace, bool kDyn>
 __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p, const FregLayout L) {
     constexpr int P = 5 + NOFF;
     constexpr int MW = (P + 31) / 32;   // in-range bitmask words (<= 3)
@@ -292,7 +299,6 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int csize = p.csize;
     const uint32_t rank = csize > 1 ? cluster_ctarank() : 0u;
-    const long long cl = blockIdx.x / csize, ncl = gridDim.x / csize;
 
     u64 *wtop = reinterpret_cast<u64 *>(smem + L.off_wtop);
     unsigned char *bh = smem + L.off_bh;                                               // [32][kHdr]
@@ -320,16 +326,60 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         cluster_wait_acquire();
     }
 
-    uint32_t load_phase = 0, round_ctr = 0, fpar = 0;
+    // ---- frames are CLAIMED, not statically assigned: a global counter hands out frame indices, so a cluster that starts
+    // late (its SMs were busy with another kernel, e.g. a concurrent NCCL collective) simply takes fewer frames instead
+    // of leaving a second wave.  Rank 0 of the cluster claims two frames ahead and broadcasts the index to its peers with
+    // st.async (completing on their claim mbarrier); a relaxed split cluster barrier (arrive at the top of a frame, wait
+    // at its end) keeps the CTAs of a cluster within one frame of each other so the two claim slots can be reused.
+    // The split barrier costs ~3 % when nothing disturbs the kernel, so clusters of more than one CTA default to the static
+    // interleaved assignment (claim_ctr == nullptr); single-CTA frames claim by default (no cluster barrier needed).
+    constexpr bool dyn = kDyn;   // compile-time: the static kernel carries none of the claim machinery
+    const uint32_t bar_claim0 = bar_load + 24;
+    volatile long long *claim_slot = reinterpret_cast<volatile long long *>(smem + 40);
+    const long long cl = blockIdx.x / csize, ncl = gridDim.x / csize;
+    if (dyn && rank == 0 && tid == 0) {
+        const long long c0 = (long long)atomicAdd(p.claim_ctr, 2ull);   // this cluster's first two frames
+        if (csize == 1) {
+            claim_slot[0] = c0;
+        } else {
+            for (int d = 0; d < csize; ++d)
+                asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(mapa_u32(smem_u32(smem + 40), (uint32_t)d)), "l"(c0) : "memory");
+        }
+    }
+    if (dyn) {
+        if (csize > 1) {
+            cluster_arrive_release();
+            cluster_wait_acquire();
+        } else {
+            __syncthreads();
+        }
+    }
+    long long f = dyn ? claim_slot[0] : cl, f_next = dyn ? f + 1 : cl + ncl;
+    __syncthreads();   // everyone has read slot 0 before a claim may overwrite it
+    if (tid == 0) {
+        mbar_init(bar_claim0, 1);
+        mbar_init(bar_claim0 + 8, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (csize > 1) {   // claim barriers are initialised cluster-wide before the first claim is sent
+        cluster_arrive_release();
+        cluster_wait_acquire();
+    }
+
+    uint32_t load_phase = 0, round_ctr = 0, fpar = 0, iter = 0;
     int tcount = 0;
     (void)tcount;
-    if (cl < p.F) request_slab(p, cl, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(p.topm_count * SLOT), sbuf);
+    if (f < p.F) request_slab(p, f, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(p.topm_count * SLOT), sbuf);
     // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
     // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
     const int lcap = min(T * CPT - p.rpc, 31);
 
-    for (long long f = cl; f < p.F; f += ncl) {
+    for (; f < p.F; f = f_next, ++iter) {
         PHNMS_TRACE(1);  // frame start
+        if (dyn && csize > 1) cluster_arrive_relaxed();
+        long long my_claim = 0;
+        if (dyn && rank == 0 && tid == 0) my_claim = (long long)atomicAdd(p.claim_ctr, 1ull);   // frame of iteration iter + 2
         // ---- staging -> registers -------------------------------------------------------------------------------
         const Slab cur = slab_geometry(p, f, rank, P);
         if (cur.bulk) {
@@ -396,11 +446,32 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         PHNMS_TRACE(3);  // rows in registers
 
         // ---- request the next frame now; it lands while this frame's rounds run ----------------------------------
-        if (f + ncl < p.F)
-            request_slab(p, f + ncl, rank, rows_buf, bar_load, tid, T, P,
+        if (!dyn) {
+            f_next = f + ncl;
+        } else if (iter > 0) {   // the frame after this one: claimed during the previous iteration, sent in its middle
+            const uint32_t cp_ = (iter - 1u) & 1u;
+            if (csize > 1) mbar_wait(bar_claim0 + 8u * cp_, ((iter - 1u) >> 1) & 1u);
+            f_next = claim_slot[cp_];
+        }
+        const bool more = f_next < p.F;   // (uniform over the cluster) another iteration follows
+        if (dyn && more && csize > 1 && tid == 0) mbar_arrive_expect_tx(bar_claim0 + 8u * (iter & 1u), 8u);
+        if (more)
+            request_slab(p, f_next, rank, rows_buf, bar_load, tid, T, P,
                          pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(p.topm_count * SLOT),
                          sbuf + (fpar ^ 1u) * sbuf_stride);
         PHNMS_TRACE(4);  // next slab requested
+        // hand the claimed frame index to the cluster; peers read it after the second barrier of their next frame
+        // (sent here, mid-frame, so that it is long there when they need it)
+        if (dyn && csize > 1) cluster_wait_plain();   // every peer has started this frame: slot (iter & 1) was consumed
+        if (dyn && more && rank == 0 && tid == 0) {
+            if (csize == 1) {
+                claim_slot[iter & 1u] = my_claim;
+            } else {
+                const uint32_t slot_a = smem_u32(smem + 40) + 8u * (iter & 1u), bar_a = bar_claim0 + 8u * (iter & 1u);
+                for (int d = 0; d < csize; ++d)
+                    st_async_b64(mapa_u32(slot_a, (uint32_t)d), (unsigned long long)my_claim, mapa_u32(bar_a, (uint32_t)d));
+            }
+        }
 
         u64 myK[CPT];
 #pragma unroll
@@ -708,6 +779,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         }
         PHNMS_TRACE(13);  // outputs written
         fpar ^= 1u;
+
     }
 
     if (csize > 1) {  // no CTA leaves while a peer may still address its shared memory

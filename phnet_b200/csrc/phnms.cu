@@ -52,7 +52,7 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
     const int P = 5 + n_off;
     const int smem_max = dev ? dev->smem_optin : 232448;
     const int sms = dev ? dev->sms : 148;
-    phnms_tuning t = {0, 0, 0, 0, 0};
+    phnms_tuning t = {0, 0, 0, 0, 0, 0};
     if (tun) t = *tun;
     pl->workspace_bytes = 0;
     pl->launches = 1;
@@ -122,7 +122,7 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
                 pl->smem_bytes = L.total;
                 pl->grid = (int)(clusters * csize);
                 pl->launches = 2;  // phnms_topm_kernel + phnms_freg_kernel
-                pl->workspace_bytes = (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 256;   // candidate block per frame (capacity)
+                pl->workspace_bytes = (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 512;   // claim counter + candidate block per frame (capacity)
                 return PHNMS_OK;
             }
             if (t.variant == PHNMS_FUSED_REG) return PHNMS_ERR_TUNING;
@@ -261,9 +261,9 @@ void fit_grid_to_occupancy(phnms_plan *pl, int64_t F, int n_off, const phnms_tun
 
 int fused_occupancy_query(const phnms_plan &pl, int n_off) {
     if (pl.variant == PHNMS_FUSED_REG) {
-        if (n_off == 72) return occupancy_clusters(phnms_freg_kernel<72, 1, false>, pl);
-        if (pl.cols_per_thread == 1) return occupancy_clusters(phnms_freg_kernel<36, 1, false>, pl);
-        return occupancy_clusters(phnms_freg_kernel<36, 2, false>, pl);
+        if (n_off == 72) return occupancy_clusters(phnms_freg_kernel<72, 1, false, false>, pl);
+        if (pl.cols_per_thread == 1) return occupancy_clusters(phnms_freg_kernel<36, 1, false, false>, pl);
+        return occupancy_clusters(phnms_freg_kernel<36, 2, false, false>, pl);
     }
     return occupancy_clusters(phnms_fused_kernel, pl);
 }
@@ -377,9 +377,17 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
         fp.trace_len = trace_len;
         fp.topm = nullptr;
         fp.topm_count = 0;
+        fp.claim_ctr = nullptr;
         if (pl.variant == PHNMS_FUSED_REG) {
             if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
-            int *topm = reinterpret_cast<int *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+            unsigned long long *claim_ctr = reinterpret_cast<unsigned long long *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+            int *topm = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(claim_ctr) + 256);
+            {   // frames are claimed dynamically by default only where that measured faster (single-CTA frames, one
+                // proposal per thread: +2.5 %); clusters pay ~3 % for the split barrier, the 2-proposal kernel ~7 %
+                const int sched = tuning ? tuning->schedule : 0;
+                const bool dynamic = sched == PHNMS_SCHED_DYNAMIC || (sched == 0 && pl.cluster == 1 && pl.cols_per_thread == 1);
+                fp.claim_ctr = dynamic ? claim_ctr : nullptr;
+            }
             // enough candidates that the first batch usually reaches top_k without an exchange
             const int topm_count = (top_k > 0 && top_k <= 4) ? 8 : kTopM;
             fp.topm_count = topm_count;
@@ -392,20 +400,26 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                     if (e2 != cudaSuccess) return (int)e2;
                 }
                 phnms_topm_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(
-                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, thresh, topm);
+                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, thresh, topm, claim_ctr);
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             fp.topm = getenv("PHNMS_NO_TOPM") ? nullptr : topm;   // debugging aid: force in-kernel candidate selection
             const FregLayout RL = freg_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
+#define PHNMS_LAUNCH_FREG(TR, DY)                                                                              \
+    do {                                                                                                       \
+        if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1, TR, DY>, pl, stream, fp, RL);            \
+        if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1, TR, DY>, pl, stream, fp, RL); \
+        return launch_cluster(phnms_freg_kernel<36, 2, TR, DY>, pl, stream, fp, RL);                            \
+    } while (0)
+            const bool dynamic = fp.claim_ctr != nullptr;
             if (trace) {   // profiling / watchdog build of the same kernel
-                if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1, true>, pl, stream, fp, RL);
-                if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1, true>, pl, stream, fp, RL);
-                return launch_cluster(phnms_freg_kernel<36, 2, true>, pl, stream, fp, RL);
+                if (dynamic) PHNMS_LAUNCH_FREG(true, true);
+                PHNMS_LAUNCH_FREG(true, false);
             }
-            if (n_off == 72) return launch_cluster(phnms_freg_kernel<72, 1, false>, pl, stream, fp, RL);
-            if (pl.cols_per_thread == 1) return launch_cluster(phnms_freg_kernel<36, 1, false>, pl, stream, fp, RL);
-            return launch_cluster(phnms_freg_kernel<36, 2, false>, pl, stream, fp, RL);
+            if (dynamic) PHNMS_LAUNCH_FREG(false, true);
+            PHNMS_LAUNCH_FREG(false, false);
+#undef PHNMS_LAUNCH_FREG
         }
         return launch_cluster(phnms_fused_kernel, pl, stream, fp);
     }

@@ -27,12 +27,14 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
                                                                     const float *__restrict__ scores,
                                                                     const int32_t *__restrict__ n_valid, long long F,
                                                                     int N, int n_off, int sort_model, int count, float thr,
-                                                                    int *__restrict__ topm) {
+                                                                    int *__restrict__ topm,
+                                                                    unsigned long long *__restrict__ claim_ctr) {
     extern __shared__ __align__(16) unsigned char smem_topm[];
     __shared__ float bit_key[kTopmWarps][32];
     __shared__ int bit_val[kTopmWarps][32];
     __shared__ int bit_ok[kTopmWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *claim_ctr = 0ull;   // the fused kernel that follows hands out frames from 0
     const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (f >= F) return;
     int n = N;

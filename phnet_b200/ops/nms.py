@@ -60,7 +60,7 @@ _ws_cache: dict = {}           # (device index, stream handle) -> reusable works
 
 
 def _workspace(L, dev, stream, F, N, n_off, t, tp):
-    key = (F, N, n_off, None if t is None else (t.path, t.cluster, t.threads, t.max_clusters, t.variant))
+    key = (F, N, n_off, None if t is None else (t.path, t.cluster, t.threads, t.max_clusters, t.variant, t.schedule))
     nbytes = _ws_bytes_cache.get(key)
     if nbytes is None:
         nbytes = _ws_bytes_cache[key] = int(L.phnms_workspace_bytes(F, N, n_off, tp))

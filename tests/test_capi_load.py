@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == set(_capi.EXPORTS), "include/phnms.h and the ctypes binding disagree"
     for s in syms:
         assert hasattr(L, s), f"libphnms.so does not export {s}"
-    assert L.phnms_abi_version() == 2
+    assert L.phnms_abi_version() == 3
 
 
 def test_library_is_sm100a_only_and_has_tma_and_cluster_code():
@@ -69,7 +69,7 @@ def test_plans():
     p = _capi.plan(16384, 1000, 72)
     assert p["path"] == _capi.PATH_FUSED and p["cluster"] * p["rows_per_cta"] >= 1000
     assert p["smem_bytes"] <= 232448 and p["grid"] % p["cluster"] == 0 and p["launches"] == 2
-    assert p["workspace_bytes"] == 16384 * 16 * (32 + 4 * 80) + 256   # per-frame block of up to 16 candidate slots
+    assert p["workspace_bytes"] == 16384 * 16 * (32 + 4 * 80) + 512   # claim counter + per-frame block of up to 16 candidate slots
     assert _capi.plan(1, 240, 72)["cluster"] == 1                       # the real OpenLane-V shape fits one CTA
     assert _capi.plan(1, 8192, 72)["path"] == _capi.PATH_FUSED          # the whole stress sweep stays on the fused path
     big = _capi.plan(1, 40000, 72)

@@ -14,6 +14,10 @@ pytestmark = pytest.mark.gpu
     (1000, 72, 4, 4096, None), (1000, 72, 0, 512, None), (1000, 36, 8, 4096, None), (240, 72, 4, 8192, None),
     (2048, 72, 4, 1024, None), (1000, 72, 4, 4096, dict(path=1, cluster=4, threads=256, variant=2)),
     (1000, 72, 4, 2048, dict(path=1, cluster=8, threads=256, variant=2)), (1000, 72, 8, 2048, dict(path=1, variant=1)),
+    # frame scheduling: clusters default to the static assignment, single-CTA frames to dynamic claiming; force the other one
+    (1000, 72, 4, 4096, dict(path=1, schedule=2)), (2048, 72, 4, 1024, dict(path=1, schedule=2)),
+    (1000, 72, 0, 300, dict(path=1, schedule=2)), (240, 72, 4, 8192, dict(path=1, schedule=1)), (1000, 36, 8, 4096, dict(path=1, schedule=1)),
+    (1000, 72, 4, 37, dict(path=1, schedule=2)), (1000, 72, 4, 3, dict(path=1, schedule=2)),
 ])
 def test_repeated_launches_are_identical_and_correct(cuda_device, N, n_off, top_k, F, tuning):
     props, scores = synth.make_frames_chunked(F, N, n_off, seed=N + n_off + top_k, device=cuda_device)
