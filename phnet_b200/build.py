@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libphnms.so")
 SOURCES = ["phnms.cu"]
-HEADERS = ["common.cuh", "fused_nms.cuh", "tiled_nms.cuh", os.path.join("..", "..", "include", "phnms.h")]
+HEADERS = ["common.cuh", "fused_nms.cuh", "fused_reg.cuh", "topm.cuh", "tiled_nms.cuh", "frontend.cuh",
+           os.path.join("..", "..", "include", "phnms.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

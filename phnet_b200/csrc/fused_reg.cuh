@@ -24,7 +24,10 @@ namespace phnms {
 constexpr int kCand = 4;   // candidates every CTA publishes per exchange (fallback batches)
 constexpr int kTopM = 16;  // capacity: per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch);
                            // FusedParams::topm_count (8 for top_k <= 4, else 16) of them are produced and fetched
-constexpr bool kDualPass = false;  // evaluate two kept lanes per pass (more ILP, but measured slower: predicate pressure)
+constexpr int kPlanLanes = 4;    // kept lanes of the planned batch evaluated per pass, one proposal per thread (n_off 72 / small frames)
+constexpr int kPlanLanes2 = 2;   // same, two proposals per thread (n_off 36): chains per thread = lanes x 2
+constexpr bool kSkipGroups = true;   // warp-uniform skip of 8-word groups outside the kept lane's own range
+constexpr bool kPackedSub = true;    // a - x of two neighbouring offsets as one FADD2 (sub.f32x2)
 constexpr int kHdr = 32;   // candidate header bytes: {key, index, start, end, mask0, mask1, mask2, aux}
 
 // A candidate slot = 32-byte header + the proposal's row padded to a multiple of 4 words.
@@ -47,7 +50,8 @@ struct FregLayout {
 
 inline FregLayout freg_layout(int rpc, int P, int csize) {
     FregLayout L;
-    int o = 64;  // mbarriers: load @0, exchange @8 / @16, frame claim @24 / @32; claimed frame indices @40 / @48
+    int o = 96;  // mbarriers: load @0, exchange @8 / @16, frame claim @24 / @32; claimed frame indices @40 / @48;
+                 // slab geometry record (Slab, 32 bytes) @64
     L.off_wtop = o;
     o += 2 * 32 * kCand * 8;
     L.off_bh = o;
@@ -82,6 +86,14 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 
+// {d0, d1} = {a0 - b0, a1 - b1}: one packed fp32x2 instruction (FADD2), each half rounded to nearest like FADD
+__device__ __forceinline__ void fsub2(float a0, float a1, float b0, float b1, float &d0, float &d1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -108,15 +120,25 @@ __device__ __forceinline__ void range_mask(int start, int end, uint32_t (&m)[MW]
     }
 }
 
-struct Slab {       // what one CTA loads for one frame (a pure function of the frame index: recomputed, not carried)
-    int nv;         // real proposals in the frame
-    int r0;         // first row owned by this CTA
-    int nloc;       // rows owned
-    int head;       // bytes between the row data and the 16-byte aligned bulk body (0,4,8,12)
-    bool bulk;      // a TMA bulk copy is in flight for it
+// What one CTA loads for one frame: its slab of rows, cut into a 16-byte aligned body (TMA bulk copies) and <= 3 words at
+// either end (plain loads).  A pure function of the frame index.  When every frame starts at the same address modulo 16
+// and has the same number of proposals (n_valid == nullptr and N * P * 4 a multiple of 16: the batch tensors PHNet and the
+// bench hand over), the record is the same for every frame: thread 0 computes it once, everybody reads it back from
+// shared memory (two LDS.128) instead of redoing ~100 instructions of 64-bit address arithmetic per warp and frame.
+struct Slab {
+    int nv;          // real proposals in the frame
+    int r0;          // first row owned by this CTA
+    int nloc;        // rows owned
+    int head;        // bytes between the row data and the 16-byte aligned bulk body (0,4,8,12)
+    uint32_t total;  // bytes of the aligned body (0: no bulk copy for the rows)
+    uint32_t chunk;  // the body is requested in pieces of this size, one per issuing warp
+    int tail0;       // first word (relative to the slab) after the aligned body
+    int ntail;       // words after the aligned body
 };
 
-__device__ __forceinline__ Slab slab_geometry(const FusedParams &p, long long f, uint32_t rank, int P) {
+__device__ __forceinline__ int slab_issuers(int T) { return (T >> 5) >= 8 ? 8 : 4; }
+
+__device__ __forceinline__ Slab slab_compute(const FusedParams &p, long long f, uint32_t rank, int P, int T) {
     Slab s;
     s.nv = p.N;
     if (p.n_valid) s.nv = max(0, min(p.n_valid[f], p.N));
@@ -125,8 +147,26 @@ __device__ __forceinline__ Slab slab_geometry(const FusedParams &p, long long f,
     const uintptr_t b = (uintptr_t)(p.props + ((size_t)f * p.N + s.r0) * P), e = b + (size_t)s.nloc * P * 4;
     const uintptr_t b_al = (b + 15) & ~(uintptr_t)15, e_al = e & ~(uintptr_t)15;
     const bool body = e_al > b_al;
-    s.bulk = body || p.topm != nullptr;
     s.head = body ? (int)(b_al - b) : 0;
+    s.total = body ? (uint32_t)(e_al - b_al) : 0u;
+    uint32_t chunk = ((s.total / (uint32_t)slab_issuers(T) + 15u) & ~15u);
+    s.chunk = chunk < 2048u ? 2048u : chunk;
+    s.tail0 = (int)((e_al - b) >> 2);
+    s.ntail = (int)((e - e_al) >> 2);
+    return s;
+}
+
+__device__ __forceinline__ bool slab_is_uniform(const FusedParams &p, int P) {
+    return p.n_valid == nullptr && (((size_t)p.N * P * 4) & 15u) == 0u;
+}
+
+__device__ __forceinline__ Slab slab_geometry(const FusedParams &p, long long f, uint32_t rank, int P, int T, bool uniform,
+                                              const unsigned char *geo) {
+    if (!uniform) return slab_compute(p, f, rank, P, T);
+    const int4 g0 = *reinterpret_cast<const int4 *>(geo), g1 = *reinterpret_cast<const int4 *>(geo + 16);
+    Slab s;
+    s.nv = g0.x; s.r0 = g0.y; s.nloc = g0.z; s.head = g0.w;
+    s.total = (uint32_t)g1.x; s.chunk = (uint32_t)g1.y; s.tail0 = g1.z; s.ntail = g1.w;
     return s;
 }
 
@@ -134,22 +174,18 @@ __device__ __forceinline__ Slab slab_geometry(const FusedParams &p, long long f,
 // either end by ordinary loads.  Call with the staging buffer free (after a __syncthreads that follows its last read).
 // When phnms_topm_kernel ran, the frame's candidate block (kTopM slots, laid out exactly like pslots) rides along as
 // one more bulk copy on the same mbarrier.
-__device__ __forceinline__ void request_slab(const FusedParams &p, long long f, uint32_t rank, unsigned char *rows_buf,
+__device__ __forceinline__ void request_slab(const FusedParams &p, long long f, const Slab &s, unsigned char *rows_buf,
                                              uint32_t bar, int tid, int T, int P, unsigned char *cand_dst,
                                              uint32_t cand_bytes, float *sbuf) {
-    const Slab s = slab_geometry(p, f, rank, P);
     const float *src = p.props + ((size_t)f * p.N + s.r0) * P;
-    const uintptr_t b = (uintptr_t)src, e = b + (size_t)s.nloc * P * 4;
-    const uintptr_t b_al = (b + 15) & ~(uintptr_t)15, e_al = e & ~(uintptr_t)15;
-    const bool body = e_al > b_al;
+    const bool body = s.total != 0u;
     const bool cand = p.topm != nullptr;
     float *rows = reinterpret_cast<float *>(rows_buf + 16 - s.head);
     // this CTA's slice of the scores: asynchronous 4-byte copies (no register is tied up while they are in flight)
     for (int c = tid; c < s.nloc; c += T) cp_async_4(smem_u32(sbuf + c), p.scores + (size_t)f * p.N + s.r0 + c);
     cp_async_commit();
     if (cand) {
-        const uint32_t slab_bytes = body ? (uint32_t)(e_al - b_al) : 0u;
-        if (tid == 0) mbar_arrive_expect_tx(bar, slab_bytes + cand_bytes);
+        if (tid == 0) mbar_arrive_expect_tx(bar, s.total + cand_bytes);
         if (tid == 32)
             bulk_g2s(smem_u32(cand_dst), reinterpret_cast<const unsigned char *>(p.topm) + (size_t)f * cand_bytes, cand_bytes, bar);
     }
@@ -159,23 +195,19 @@ __device__ __forceinline__ void request_slab(const FusedParams &p, long long f, 
         // streaming stores to HBM: 2.3k cycles per frame in the phase trace).  The copy is cut into up to 8 chunks,
         // each issued by lane 0 of a different warp (back-to-back UBLKCPs from one thread serialise on the TMA queue
         // and sat on the critical path); a chunk may complete before thread 0 has armed the barrier, which is fine.
-        const uint32_t total = (uint32_t)(e_al - b_al);
-        if (tid == 0 && !cand) mbar_arrive_expect_tx(bar, total);
+        if (tid == 0 && !cand) mbar_arrive_expect_tx(bar, s.total);
         {
-            const int nw = T >> 5, issuers = nw < 8 ? nw : 8;
-            uint32_t chunk = ((total / issuers + 15) & ~15u);
-            if (chunk < 2048u) chunk = 2048u;
+            const int nw = T >> 5, issuers = slab_issuers(T);
             const int w = (tid >> 5), k = nw - 1 - w;   // last warps issue: warp 0 has the first-batch work ahead of it
             if ((tid & 31) == 0 && k < issuers) {
-                const uint32_t off = (uint32_t)k * chunk;
-                if (off < total)
-                    bulk_g2s(smem_u32(rows_buf + 16) + off, reinterpret_cast<const void *>(b_al + off),
-                             min(chunk, total - off), bar);
+                const uint32_t off = (uint32_t)k * s.chunk;
+                if (off < s.total)
+                    bulk_g2s(smem_u32(rows_buf + 16) + off, reinterpret_cast<const unsigned char *>(src) + s.head + off,
+                             min(s.chunk, s.total - off), bar);
             }
         }
-        const int tail0 = (int)((e_al - b) >> 2), ntail = (int)((e - e_al) >> 2);
         if (tid >= 32 && tid - 32 < (s.head >> 2)) rows[tid - 32] = src[tid - 32];
-        if (tid >= 64 && tid - 64 < ntail) rows[tail0 + tid - 64] = src[tail0 + tid - 64];
+        if (tid >= 64 && tid - 64 < s.ntail) rows[s.tail0 + tid - 64] = src[s.tail0 + tid - 64];
     } else {
         for (int w = tid; w < s.nloc * P; w += T) rows[w] = src[w];
     }
@@ -201,6 +233,9 @@ __device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, con
     bool act[NK][CPT];
     int len[NK][CPT];
     bool any_act = false, hdr_terms = false;
+    uint32_t um_l[MW];   // union of the kept lanes' own in-range masks (the same value in every thread)
+#pragma unroll
+    for (int w = 0; w < MW; ++w) um_l[w] = 0u;
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
         const uint4 wh = *reinterpret_cast<const uint4 *>(hdr[k]);
@@ -209,6 +244,8 @@ __device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, con
         const int sa = (int)wh.z, ea = (int)wh.w;
         const uint32_t ma[3] = {wm.x, wm.y, wm.z};
         a_addr[k] = smem_u32(hdr[k] + kHdr);
+#pragma unroll
+        for (int w = 0; w < MW; ++w) um_l[w] |= ma[w];
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int start = max(sa, st[c]);   // nms_kernel.cu:31
@@ -232,6 +269,9 @@ __device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, con
         }
     }
     if (__any_sync(0xffffffffu, any_act)) {
+        uint32_t um[MW];
+#pragma unroll
+        for (int w = 0; w < MW; ++w) um[w] = kSkipGroups ? __reduce_or_sync(0xffffffffu, um_l[w]) : 0xffffffffu;
         if (__any_sync(0xffffffffu, hdr_terms)) {
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
@@ -246,25 +286,45 @@ __device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, con
                     }
             }
         }
+        // Row words are walked in groups of 8 (two LDS.128 of the kept row).  A group in which no kept lane of this pass
+        // has an in-range word is skipped by the whole warp: the pair mask is a subset of the kept lane's own mask
+        // (also on the wrapped-counter path: [i0, last] lies inside [0, 5+ea]), so nothing would be added there.  `um`
+        // comes out of REDUX in a uniform register, which makes these warp-uniform branches (no reconvergence code).
+        // The subtractions of two neighbouring offsets are one packed FADD2 (sub.f32x2, round-to-nearest per element,
+        // no FTZ: bit-identical to two FADDs); the sum itself stays the reference's sequential fp32 chain (:38-44).
 #pragma unroll
-        for (int g = 1; g < P4 / 4; ++g) {
-            float a4[NK][4];
+        for (int q = 0; q < (P4 + 7) / 8; ++q) {
+            if (kSkipGroups && ((um[(8 * q) >> 5] >> ((8 * q) & 31)) & 0xffu) == 0u) continue;
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const float4 av = lds_v4(a_addr[k] + 16 * g);
-                a4[k][0] = av.x; a4[k][1] = av.y; a4[k][2] = av.z; a4[k][3] = av.w;
-            }
+            for (int h = 0; h < 2; ++h) {
+                const int g = 2 * q + h;
+                if (g >= 1 && g < P4 / 4) {
+                    float a4[NK][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = 4 * g + u;
-                if (i >= 5 && i < P) {
+                    for (int k = 0; k < NK; ++k) {
+                        const float4 av = lds_v4(a_addr[k] + 16 * g);
+                        a4[k][0] = av.x; a4[k][1] = av.y; a4[k][2] = av.z; a4[k][3] = av.w;
+                    }
 #pragma unroll
-                    for (int k = 0; k < NK; ++k)
+                    for (int u = 0; u < 4; u += 2) {
+                        const int i = 4 * g + u;
+                        const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
 #pragma unroll
-                        for (int c = 0; c < CPT; ++c) {
-                            const float t = __fsub_rn(a4[k][u], x[c][i - 5]);
-                            if (m[k][c][i >> 5] & (1u << (i & 31))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t));
-                        }
+                        for (int k = 0; k < NK; ++k)
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                float t0 = 0.0f, t1 = 0.0f;
+                                if (kPackedSub && v0 && v1) {
+                                    fsub2(a4[k][u], a4[k][u + 1], x[c][v0 ? i - 5 : 0], x[c][v1 ? i - 4 : 0], t0, t1);
+                                } else {
+                                    if (v0) t0 = __fsub_rn(a4[k][u], x[c][v0 ? i - 5 : 0]);
+                                    if (v1) t1 = __fsub_rn(a4[k][u + 1], x[c][v1 ? i - 4 : 0]);
+                                }
+                                if (v0 && (m[k][c][i >> 5] & (1u << (i & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t0));
+                                if (v1 && (m[k][c][(i + 1) >> 5] & (1u << ((i + 1) & 31))))
+                                    dist[k][c] = __fadd_rn(dist[k][c], fabsf(t1));
+                            }
+                    }
                 }
             }
         }
@@ -276,6 +336,99 @@ __device__ __forceinline__ void freg_eval(const FusedParams &p, long long f, con
             const bool hit = act[k][c] && (dist[k][c] < __fmul_rn(p.thr, (float)len[k][c]));  // :46
             hit_out[k][c] = hit;
             if (hit || myK[c] == wk[k]) par[c] = (uint32_t)(n_base + k + 1);                  // :127,:129
+        }
+}
+
+// The planned first batch knows ALL of its kept lanes before a column is touched, so they are evaluated in ONE pass over
+// the registers: NK independent fp32 chains per proposal (each still the reference's ascending sequential sum, :38-44)
+// instead of NK passes with one chain each.  A pass with a single chain is latency bound -- 72 dependent FADDs, 4 warps
+// per scheduler (ncu: issue slots 53 % busy, top stall "wait") -- NK chains hide that latency and the per-pass set-up
+// and tail are paid once.  Row word i of kept lane k enters proposal c's sum iff bit i of (ma_k & mb_c) is set: the
+// pair's range [max(sa,sb), min(ea,eb)] is the intersection of the two lanes' own ranges.  That identity needs
+// max(sa,sb) >= 0 (below, header words or the wrapped unsigned-char counter come into play, :38): if any active pair
+// of the warp has a negative start, the warp takes the exact one-lane-per-pass evaluator instead (rare).
+// Lanes that are not "active" for a kept lane (ranked before it, empty range) accumulate a value nobody reads.
+template <int NOFF, int CPT, int NK, typename HdrFn>
+__device__ __forceinline__ void freg_eval_multi(const FusedParams &p, long long f, const unsigned char *const (&hdr)[NK],
+                                                int nk, const bool (&live)[CPT], const u64 (&myK)[CPT],
+                                                const int (&st)[CPT], const int (&en)[CPT],
+                                                const uint32_t (&mb)[CPT][(5 + NOFF + 31) / 32], const float (&x)[CPT][NOFF],
+                                                HdrFn my_hdr, uint32_t (&par)[CPT], long long n_base) {
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3;
+    u64 wk[NK];
+    int sa[NK], ea[NK];
+    uint32_t a_addr[NK];
+    bool rare = false;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const uint4 wh = *reinterpret_cast<const uint4 *>(hdr[k]);
+        wk[k] = k < nk ? (((u64)wh.x << 32) | wh.y) : kNone64;   // a padding lane activates nobody
+        sa[k] = (int)wh.z;
+        ea[k] = (int)wh.w;
+        a_addr[k] = smem_u32(hdr[k] + kHdr);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+            rare |= live[c] && (myK[c] > wk[k]) && (min(ea[k], en[c]) >= max(sa[k], st[c])) && (max(sa[k], st[c]) < 0);
+    }
+    if (__any_sync(0xffffffffu, rare)) {
+        for (int k = 0; k < nk; ++k) {
+            const unsigned char *const hh[1] = {hdr[k]};
+            bool hit[1][CPT];
+            freg_eval<NOFF, CPT, 1>(p, f, hh, live, myK, st, en, mb, x, my_hdr, par, hit, n_base + k);
+        }
+        return;
+    }
+    float dist[NK][CPT];
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) dist[k][c] = 0.0f;
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        uint32_t m[NK][CPT];   // pair masks of this 32-word span
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const uint32_t ma = *reinterpret_cast<const uint32_t *>(hdr[k] + 16 + 4 * w);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) m[k][c] = ma & mb[c][w];
+        }
+#pragma unroll
+        for (int g = 8 * w; g < 8 * w + 8; ++g) {
+            if (g >= 1 && g < P4 / 4) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const float4 av = lds_v4(a_addr[k] + 16 * g);
+                    const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u += 2) {
+                        const int i = 4 * g + u;
+                        const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            float t0 = 0.0f, t1 = 0.0f;
+                            if (v0 && v1) {
+                                fsub2(a4[u], a4[u + 1], x[c][v0 ? i - 5 : 0], x[c][v1 ? i - 4 : 0], t0, t1);
+                            } else {
+                                if (v0) t0 = __fsub_rn(a4[u], x[c][v0 ? i - 5 : 0]);
+                                if (v1) t1 = __fsub_rn(a4[u + 1], x[c][v1 ? i - 4 : 0]);
+                            }
+                            if (v0 && (m[k][c] & (1u << (i & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t0));
+                            if (v1 && (m[k][c] & (1u << ((i + 1) & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t1));
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k)      // in keep order: the last kept lane that covers a proposal wins (:127)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int start = max(sa[k], st[c]), end = min(ea[k], en[c]);                  // :31,:34
+            const bool act = live[c] && (myK[c] > wk[k]) && (end >= start);                 // :36
+            const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
+            const bool hit = act && (dist[k][c] < __fmul_rn(p.thr, (float)len));            // :46
+            if (k < nk && (hit || myK[c] == wk[k])) par[c] = (uint32_t)(n_base + k + 1);    // :127,:129
         }
 }
 
@@ -370,7 +523,18 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
     uint32_t load_phase = 0, round_ctr = 0, fpar = 0, iter = 0;
     int tcount = 0;
     (void)tcount;
-    if (f < p.F) request_slab(p, f, rank, rows_buf, bar_load, tid, T, P, pslots, (uint32_t)(p.topm_count * SLOT), sbuf);
+    // slab geometry: identical for every frame in the common case (see Slab), then kept in shared memory
+    const bool geo_uniform = slab_is_uniform(p, P);
+    const unsigned char *geo = smem + 64;
+    if (geo_uniform && tid == 0) {
+        const Slab s0 = slab_compute(p, 0, rank, P, T);
+        *reinterpret_cast<int4 *>(smem + 64) = make_int4(s0.nv, s0.r0, s0.nloc, s0.head);
+        *reinterpret_cast<int4 *>(smem + 80) = make_int4((int)s0.total, (int)s0.chunk, s0.tail0, s0.ntail);
+    }
+    __syncthreads();
+    if (f < p.F)
+        request_slab(p, f, slab_geometry(p, f, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P, pslots,
+                     (uint32_t)(p.topm_count * SLOT), sbuf);
     // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
     // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
     const int lcap = min(T * CPT - p.rpc, 31);
@@ -381,8 +545,8 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         long long my_claim = 0;
         if (dyn && rank == 0 && tid == 0) my_claim = (long long)atomicAdd(p.claim_ctr, 1ull);   // frame of iteration iter + 2
         // ---- staging -> registers -------------------------------------------------------------------------------
-        const Slab cur = slab_geometry(p, f, rank, P);
-        if (cur.bulk) {
+        const Slab cur = slab_geometry(p, f, rank, P, T, geo_uniform, geo);
+        if (cur.total != 0u || p.topm != nullptr) {
             if (kTrace && p.trace_len < 0) mbar_wait_watch(bar_load, load_phase, p.trace, 1, f, round_ctr);
             else mbar_wait(bar_load, load_phase);
             load_phase ^= 1u;
@@ -456,7 +620,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         const bool more = f_next < p.F;   // (uniform over the cluster) another iteration follows
         if (dyn && more && csize > 1 && tid == 0) mbar_arrive_expect_tx(bar_claim0 + 8u * (iter & 1u), 8u);
         if (more)
-            request_slab(p, f_next, rank, rows_buf, bar_load, tid, T, P,
+            request_slab(p, f_next, slab_geometry(p, f_next, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P,
                          pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(p.topm_count * SLOT),
                          sbuf + (fpar ^ 1u) * sbuf_stride);
         PHNMS_TRACE(4);  // next slab requested
@@ -506,28 +670,29 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             }
             auto real_hdr = [&](int c) { return p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P; };
             while (kept) {
-                const int i0 = __ffs(kept) - 1;
-                kept &= kept - 1u;
-                const int i1 = (kDualPass && kept) ? __ffs(kept) - 1 : -1;   // second lane of this pass (if dual passes are on)
-                if (i1 >= 0) kept &= kept - 1u;
-                const unsigned char *h0 = csl + (size_t)i0 * L.slot_stride;
-                if (rank == 0 && tid == 0) {                                                       // :118
-                    p.keep[(size_t)f * p.N + n] = (long long)reinterpret_cast<const uint32_t *>(h0)[1];
-                    if (i1 >= 0)
-                        p.keep[(size_t)f * p.N + n + 1] =
-                            (long long)reinterpret_cast<const uint32_t *>(csl + (size_t)i1 * L.slot_stride)[1];
+                constexpr int NKP = CPT == 1 ? kPlanLanes : kPlanLanes2;
+                const unsigned char *hh[NKP];
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < NKP; ++k) {
+                    const int i = kept ? __ffs(kept) - 1 : -1;
+                    if (i >= 0) {
+                        kept &= kept - 1u;
+                        ++cnt;
+                    }
+                    hh[k] = csl + (size_t)max(i, 0) * L.slot_stride;   // padding lanes point at a valid slot and are ignored
+                    if (i >= 0 && rank == 0 && tid == 0)                // :118
+                        p.keep[(size_t)f * p.N + n + k] = (long long)reinterpret_cast<const uint32_t *>(hh[k])[1];
                 }
-                if (i1 >= 0) {
-                    const unsigned char *const hh[2] = {h0, csl + (size_t)i1 * L.slot_stride};
-                    bool hit[2][CPT];
-                    freg_eval<NOFF, CPT, 2>(p, f, hh, real, myK, st, en, mb, x, real_hdr, par, hit, n);
-                    n += 2;
-                } else {
-                    const unsigned char *const hh[1] = {h0};
+                if (NKP == 1) {
+                    const unsigned char *const h1[1] = {hh[0]};
                     bool hit[1][CPT];
-                    freg_eval<NOFF, CPT, 1>(p, f, hh, real, myK, st, en, mb, x, real_hdr, par, hit, n);
-                    n += 1;
+                    freg_eval<NOFF, CPT, 1>(p, f, h1, real, myK, st, en, mb, x, real_hdr, par, hit, n);
+                } else {
+                    const unsigned char *const (&hc)[NKP] = hh;
+                    freg_eval_multi<NOFF, CPT, NKP>(p, f, hc, cnt, real, myK, st, en, mb, x, real_hdr, par, n);
                 }
+                n += cnt;
             }
             PHNMS_TRACE(11);  // planned batch done
             // done when top_k lanes are kept, or when every lane of the frame was a candidate

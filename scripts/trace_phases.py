@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from phnet_b200 import _capi, synth
 
 N = int(os.environ.get("N", 1000)); n_off = int(os.environ.get("NOFF", 72)); F = int(os.environ.get("F", 4736))
-tune = _capi.tuning(path=1, cluster=int(os.environ.get("CLUSTER", 2)), threads=int(os.environ.get("THREADS", 512)), variant=2)
+tune = _capi.tuning(path=1, cluster=int(os.environ.get("CLUSTER", 2)), threads=int(os.environ.get("THREADS", 512)), variant=2, max_clusters=int(os.environ.get("MAXC", 0)))
 dev = torch.device("cuda:0")
 props, scores = synth.make_frames_chunked(F, N, n_off, seed=0, device=dev)
 keep = torch.empty((F, N), dtype=torch.int64, device=dev); num = torch.empty((F,), dtype=torch.int64, device=dev)

@@ -90,6 +90,17 @@ def test_edge_frames(cuda_device, n_off):
                              ctx=f"edge seed={seed} No={n_off} top_k={top_k} thr={thr} tuning={tuning}")
 
 
+def test_subnormal_offsets(cuda_device):
+    """fp32 subnormals must survive on every path (no flush-to-zero): the reference's FADDs keep them, and so must the
+    packed sub.f32x2 of the register-resident kernel.  A flushed difference would read as distance 0 and suppress."""
+    for n_off in (72, 36):
+        props, scores = synth.make_frames(4, 300, n_off, seed=11)
+        props[..., 5:] *= 1e-41          # |dx| <= 767e-41 = 7.7e-39 < FLT_MIN: every difference and sum is subnormal
+        for thr in (50e-41, 5e-41, 1e-45):
+            for tuning in (None, dict(path=1, variant=1), dict(path=2)):
+                run_both(props, scores, thr, 4, cuda_device, tuning=tuning, ctx=f"subnormal No={n_off} thr={thr} tuning={tuning}")
+
+
 def test_score_ties_all_sort_models(cuda_device):
     for N in (5, 20, 32, 33, 100, 128, 129, 600):
         props, scores = synth.make_frames(5, N, 72, seed=N, ties=True)
