@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--max-clusters", type=int, default=0)
     ap.add_argument("--path", type=int, default=0)
+    ap.add_argument("--collect", default="peer", choices=["peer", "nccl"], help="N > 1: how the kept lanes are collected")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -226,18 +227,42 @@ def run_ours(a):
              torch.empty((F, N), dtype=torch.int64, device=dev)) for _ in range(2)]
     gathered = [None]
 
+    # Final collection of the kept lanes (the path's only exchange).  Preferred: the NMS kernel itself stores every frame's
+    # compact record into the result buffer of EVERY rank through peer memory (NVLink / NVSwitch, phnet_b200/peer.py); a
+    # one-warp flag kernel per step signals completion and waits for the previous step of all ranks.  If peer memory
+    # cannot be set up on this box: one NCCL all-gather per step on the compute stream (a side stream would take an SM
+    # away from the persistent NMS kernel).
+    collector, collection = None, "none (single GPU)"
+    if world > 1 and a.collect != "nccl":
+        try:
+            from phnet_b200 import peer
+            collector = peer.PeerCollector(F, a.top_k + 1, nbuf=3)
+            collection = "kernel stores into every rank's buffer over peer memory (CUDA IPC + NVLink), flag kernel per step"
+        except Exception as e:   # noqa: BLE001 -- report why, fall back to the collective
+            collection = f"NCCL all_gather_into_tensor per step (peer memory unavailable: {type(e).__name__}: {e})"
+    elif world > 1:
+        collection = "NCCL all_gather_into_tensor per step (requested)"
+    step_no = [0]
+
     def step(i, ev_pair=None):
         b = i & 1
         cur = torch.cuda.current_stream(dev)
+        step_no[0] += 1
+        e = step_no[0]
         if ev_pair is not None:
             ev_pair[0].record(cur)
-        nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b])
+        if collector is not None:
+            nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b], collect=collector.collect_arg(e % 3))
+        else:
+            nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b])
         if ev_pair is not None:
             ev_pair[1].record(cur)
-        if world > 1:
-            # Final collection of the kept lanes: one all-gather over NVLink per step, enqueued on the SAME stream.  (On a
-            # side stream the NCCL kernel takes an SM away from the persistent NMS kernel whose grid fills the GPU; the
-            # displaced cluster then only starts when another one has finished all of its frames and the step takes 2x.)
+        if collector is not None:
+            # records of step e are on their way to every rank; those of step e-1 are complete everywhere when this returns.
+            # (Buffer e % 3 is next written by step e + 3, which every rank launches after it has seen epoch e + 1 of all.)
+            collector._sync(e, e - 1, 10.0)
+            gathered[0] = collector.gathered((e - 1) % 3)
+        elif world > 1:
             packed = sharding.pack_kept(outs[b][0], outs[b][1], a.top_k)
             gathered[0] = sharding.gather_kept(packed, F * world)
 
@@ -261,6 +286,16 @@ def run_ours(a):
         fence()
     ms_total = e0.elapsed_time(e1)
     kern_ms = statistics.mean(p0.elapsed_time(p1) for p0, p1 in pairs)
+    if collector is not None:
+        # the last step's records: wait for them, then check the gathered buffer against this rank's own results
+        collector.wait(step_no[0])
+        torch.cuda.synchronize(dev)
+        if collector.status() != 0:
+            raise SystemExit(f"bench.py: peer collection timed out waiting for rank {collector.status() - 1}")
+        last = collector.gathered(step_no[0] % 3)
+        mine = sharding.pack_kept(outs[(a.steps - 1) & 1][0], outs[(a.steps - 1) & 1][1], a.top_k)
+        assert torch.equal(last[rank * F:(rank + 1) * F], mine), "collected records differ from this rank's keep / num"
+        assert bool((last[:, a.top_k] >= 1).all()), "a rank's records are missing from the gathered buffer"
     if world > 1:
         t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -322,7 +357,8 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "frames_per_gpu_per_step": F, "global_frames_per_step": F * world,
                        "proposals": N, "offsets": n_off, "overlap": a.overlap, "top_k": a.top_k,
                        "l2": f"inputs are {F * N * (6 + n_off) * 4 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
-                       "parallelism": f"frames sharded x{world}; no data-path collective; kept lanes all-gathered (NCCL) once per step" if world > 1 else "single GPU",
+                       "parallelism": f"frames sharded x{world}; no data-path collective; kept lanes collected on every rank once per step" if world > 1 else "single GPU",
+                       "collection": collection,
                        "plan": plan},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(N, n_off, F), "peak_source": peak_src,
@@ -330,7 +366,7 @@ def run_ours(a):
                                     else "phnms_fused_kernel" if plan["path"] == 1 else "phnms_order/mask/scan kernels"),
                          "kernel_ms_per_launch": kern_ms},
             "clocks": clocks.summary(),
-            "gpu_launches": a.steps * plan["launches"],
+            "gpu_launches": a.steps * (plan["launches"] + (2 if collector is not None else 0)),
         }
         if e2e is not None:
             line["e2e"] = e2e
@@ -340,6 +376,8 @@ def run_ours(a):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+    if collector is not None:
+        collector.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

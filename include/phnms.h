@@ -3,9 +3,9 @@
  *
  * This is the drop-in boundary for PHNet's `libs/ops` lane NMS.  Every entry point takes plain
  * pointers and sizes (no torch types); device pointers are raw CUDA device addresses and `stream`
- * is a `cudaStream_t` passed as `void*`.  The library never allocates or frees device memory and
- * never synchronises the stream: all buffers belong to the caller (PyTorch in the Python mirror,
- * phnet_b200/ops/nms.py).
+ * is a `cudaStream_t` passed as `void*`.  The compute entry points never allocate or free device
+ * memory and never synchronise the stream: all buffers belong to the caller (PyTorch in the Python
+ * mirror, phnet_b200/ops/nms.py).  The only allocating calls are the explicit phnms_peer_* helpers.
  *
  * Reference interfaces replaced (paths relative to the PHNet repository):
  *   libs/ops/nms.py:32-33          nms(boxes, scores, overlap, top_k)
@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PHNMS_ABI_VERSION 3
+#define PHNMS_ABI_VERSION 4
 
 #define PHNMS_OK 0
 #define PHNMS_ERR_BAD_ARG (-1)      /* null pointer, negative size, misaligned pointer                         */
@@ -114,6 +114,54 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                             int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
                             int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream,
                             int64_t *trace, int trace_len);
+
+/*
+ * Lane NMS + collection of the kept lanes (the multi-GPU "final collection" of the kept-lane results, done with plain
+ * stores over peer memory instead of a collective).  Same as phnms_forward_f32; in addition the compact record of frame f,
+ *     int64[top_k + 1] = { keep[f, 0 .. top_k-1] zero padded, num_keep[f] },
+ * is stored at row (row0 + f) of each of the n_dst destination buffers ([rows, top_k + 1] int64).  A destination is any
+ * address the current device can store to: local memory, or another GPU's buffer mapped into this process
+ * (phnms_peer_open) -- then the records travel over NVLink / NVSwitch.  With every rank passing the buffers of all ranks
+ * and row0 = rank * F, each rank ends up holding the records of all frames: an all-gather without a collective call
+ * (one extra ~2 us launch in the same call).  Requires top_k >= 1.  Completion across GPUs: phnms_peer_sync.
+ */
+#define PHNMS_MAX_DST 16
+typedef struct phnms_collect {
+    int n_dst;                        /* destinations, 1 .. PHNMS_MAX_DST                              */
+    int reserved;
+    int64_t row0;                     /* row of this call's frame 0 in every destination               */
+    int64_t *dst[PHNMS_MAX_DST];      /* device-accessible [rows, top_k + 1] int64 buffers, 8-byte aligned */
+} phnms_collect;
+
+int phnms_forward_collect_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
+                              int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
+                              int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning /* nullable */,
+                              void *stream, const phnms_collect *collect);
+
+/*
+ * Peer-memory plumbing for the collection above (one process per GPU, one node).  These are the only entry points that
+ * allocate: phnms_peer_alloc makes a dedicated, zero-filled cudaMalloc allocation on the current device and returns its
+ * CUDA IPC handle (64 bytes, to be sent to the other ranks by any host channel); phnms_peer_open maps another rank's
+ * allocation into this process (enabling peer access), phnms_peer_close unmaps it, phnms_peer_free releases one's own.
+ */
+#define PHNMS_IPC_HANDLE_BYTES 64
+int phnms_peer_alloc(size_t bytes, void **ptr, unsigned char *handle /* [PHNMS_IPC_HANDLE_BYTES] out */);
+int phnms_peer_open(const unsigned char *handle /* [PHNMS_IPC_HANDLE_BYTES] */, void **ptr);
+int phnms_peer_close(void *ptr);
+int phnms_peer_free(void *ptr);
+
+/*
+ * Cross-GPU completion flags, enqueued on `stream` (one tiny kernel, asynchronous).  Every rank owns an array of n
+ * uint64 flags in peer-mapped memory.
+ *   signal_epoch != 0: store it (system-scope release) to signal_dst[d] for d < n -- this rank's slot in rank d's array.
+ *                      Ordered after everything earlier work of this stream stored to those peers.
+ *   wait_epoch   != 0: spin until wait_src[r] >= wait_epoch for all r < n (system-scope acquire) -- every rank has
+ *                      signalled that epoch -- or until timeout_ns (0 = 10 s) has passed; on timeout *status (device int,
+ *                      nullable) is set to 1 + the index of the slot that did not arrive and the kernel returns.
+ * Epochs must increase from call to call (flags are never reset).
+ */
+int phnms_peer_sync(uint64_t *const *signal_dst /* host array [n] of device pointers */, const uint64_t *wait_src, int n,
+                    uint64_t signal_epoch, uint64_t wait_epoch, uint64_t timeout_ns, int *status, void *stream);
 
 /*
  * The ordering alone (libs/ops/csrc/nms.cpp:51): order[f, i] = original index of the i-th proposal of frame f

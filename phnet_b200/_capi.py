@@ -16,7 +16,11 @@ EXPORTS = (
     "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query",
     "phnms_forward_f32", "phnms_forward_f32_trace", "phnms_order_workspace_bytes", "phnms_order_f32",
     "phnms_get_lanes_workspace_bytes", "phnms_get_lanes_f32",
+    "phnms_forward_collect_f32", "phnms_peer_alloc", "phnms_peer_open", "phnms_peer_close", "phnms_peer_free", "phnms_peer_sync",
 )
+ABI_VERSION = 4
+MAX_DST = 16
+IPC_HANDLE_BYTES = 64
 
 
 class Tuning(ctypes.Structure):
@@ -32,6 +36,22 @@ class Plan(ctypes.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Collect(ctypes.Structure):
+    """phnms_collect: where the compact kept-lane records of a call go (include/phnms.h)."""
+    _fields_ = [("n_dst", ctypes.c_int), ("reserved", ctypes.c_int), ("row0", ctypes.c_int64),
+                ("dst", ctypes.c_void_p * MAX_DST)]
+
+
+def collect(dst_ptrs, row0: int = 0) -> Collect:
+    if not 1 <= len(dst_ptrs) <= MAX_DST:
+        raise ValueError(f"between 1 and {MAX_DST} collection buffers")
+    c = Collect()
+    c.n_dst, c.reserved, c.row0 = len(dst_ptrs), 0, int(row0)
+    for i, ptr in enumerate(dst_ptrs):
+        c.dst[i] = int(ptr)
+    return c
 
 
 class PhnmsError(RuntimeError):
@@ -76,7 +96,23 @@ def lib() -> ctypes.CDLL:
     L.phnms_order_workspace_bytes.restype = sz
     L.phnms_order_f32.argtypes = [vp, vp, i64, i64, ci, vp, vp, sz, vp]
     L.phnms_order_f32.restype = ci
-    if L.phnms_abi_version() != 3 and not os.environ.get("PHNMS_SO"):
+    try:
+        L.phnms_forward_collect_f32.argtypes = L.phnms_forward_f32.argtypes + [ctypes.POINTER(Collect)]
+        L.phnms_forward_collect_f32.restype = ci
+        L.phnms_peer_alloc.argtypes = [sz, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.phnms_peer_alloc.restype = ci
+        L.phnms_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.phnms_peer_open.restype = ci
+        L.phnms_peer_close.argtypes = [vp]
+        L.phnms_peer_close.restype = ci
+        L.phnms_peer_free.argtypes = [vp]
+        L.phnms_peer_free.restype = ci
+        L.phnms_peer_sync.argtypes = [ctypes.POINTER(vp), vp, ci, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
+        L.phnms_peer_sync.restype = ci
+    except AttributeError:      # an older build loaded through PHNMS_SO for A/B timing: no collection entry points
+        if not os.environ.get("PHNMS_SO"):
+            raise
+    if L.phnms_abi_version() != ABI_VERSION and not os.environ.get("PHNMS_SO"):
         raise ImportError("libphnms.so ABI version mismatch; rebuild with `python -m phnet_b200.build`")
     _lib = L
     return L

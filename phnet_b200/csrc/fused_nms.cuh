@@ -32,6 +32,8 @@ struct FusedLayout {
     int total;
 };
 
+constexpr int kMaxCollectDst = 16;   // == PHNMS_MAX_DST
+
 struct FusedParams {
     const float *props;
     const float *scores;

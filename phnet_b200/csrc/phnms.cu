@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "fused_nms.cuh"
 #include "fused_reg.cuh"
@@ -268,6 +269,63 @@ int fused_occupancy_query(const phnms_plan &pl, int n_off) {
     return occupancy_clusters(phnms_fused_kernel, pl);
 }
 
+// Compact kept-lane records: one thread per (frame, column) reads keep / num_keep of the call that has just been enqueued
+// and stores the value to every destination (local memory or peer GPUs' buffers, then over NVLink).  A separate 2 us
+// launch rather than an epilogue of the NMS kernels: the register-resident kernel sits exactly at its 128-register cap and
+// any addition to it costs spills in its frame loop (measured: -16 %).
+struct CollectArgs {
+    int n;
+    long long row0;
+    long long *dst[kMaxCollectDst];
+};
+
+__global__ void phnms_collect_kernel(const long long *__restrict__ keep, const long long *__restrict__ num, long long F,
+                                     int N, int top_k, CollectArgs ca) {
+    const int w = top_k + 1;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * w) return;
+    const long long f = i / w;
+    const int c = (int)(i - f * w);
+    const long long cnt = num[f];
+    const long long v = c == w - 1 ? cnt : ((c < cnt && c < N) ? keep[f * N + c] : 0ll);
+    for (int d = 0; d < ca.n; ++d) ca.dst[d][(ca.row0 + f) * w + c] = v;
+}
+
+// Cross-GPU completion of a collection step.  Every rank owns a flag array (one u64 per rank) in peer-mapped memory.
+// signal: store `epoch` into this rank's slot of every peer's array (system-scope release: ordered after the records the
+//         preceding kernels of this stream wrote to the same peers);
+// wait:   spin until every slot of the local array has reached `epoch` (system-scope acquire), give up after `timeout_ns`.
+struct PeerSyncArgs {
+    int n;
+    unsigned long long signal_epoch, wait_epoch, timeout_ns;
+    unsigned long long *signal_dst[kMaxCollectDst];
+    const unsigned long long *wait_src;
+    int *status;
+};
+
+__global__ void phnms_peer_sync_kernel(PeerSyncArgs a) {
+    const int t = threadIdx.x;
+    if (t >= a.n) return;
+    if (a.signal_epoch) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.signal_dst[t]), "l"(a.signal_epoch) : "memory");
+    }
+    if (a.wait_epoch) {
+        unsigned long long t0, now, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_src + t) : "memory");
+            if (v >= a.wait_epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > a.timeout_ns) {
+                if (a.status) atomicExch(a.status, 1 + t);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -325,17 +383,52 @@ int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int6
     return (int)cudaGetLastError();
 }
 
+static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
+                        float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
+                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len,
+                        const phnms_collect *collect);
+
 int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                       float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
                       void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_) {
-    return phnms_forward_f32_trace(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent,
-                                   ws, ws_bytes, tuning, stream_, nullptr, 0);
+    return forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
+                        tuning, stream_, nullptr, 0, nullptr);
 }
 
 int phnms_forward_f32_trace(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
                             int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
                             int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_,
                             int64_t *trace, int trace_len) {
+    return forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
+                        tuning, stream_, trace, trace_len, nullptr);
+}
+
+int phnms_forward_collect_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
+                              int n_off, float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep,
+                              int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_,
+                              const phnms_collect *collect) {
+    if (!collect) return PHNMS_ERR_BAD_ARG;
+    if (collect->n_dst < 1 || collect->n_dst > PHNMS_MAX_DST || collect->row0 < 0 || top_k < 1 || top_k > 0x7ffffff)
+        return PHNMS_ERR_BAD_ARG;
+    for (int d = 0; d < collect->n_dst; ++d)
+        if (!collect->dst[d] || ((uintptr_t)collect->dst[d] & 7u)) return PHNMS_ERR_BAD_ARG;
+    int rc = forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws,
+                          ws_bytes, tuning, stream_, nullptr, 0, collect);
+    if (rc != PHNMS_OK || F == 0) return rc;
+    CollectArgs ca;
+    ca.n = collect->n_dst;
+    ca.row0 = collect->row0;
+    for (int d = 0; d < kMaxCollectDst; ++d) ca.dst[d] = d < collect->n_dst ? reinterpret_cast<long long *>(collect->dst[d]) : nullptr;
+    const long long total = (long long)F * (top_k + 1);
+    phnms_collect_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        reinterpret_cast<const long long *>(keep), reinterpret_cast<const long long *>(num_keep), F, (int)N, (int)top_k, ca);
+    return (int)cudaGetLastError();
+}
+
+static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
+                        float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
+                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len,
+                        const phnms_collect *collect) {
     int rc = check_shape(F, N, n_off);
     if (rc != PHNMS_OK) return rc;
     if (sort_model < 0 || sort_model > 2 || top_k < 0) return PHNMS_ERR_BAD_ARG;
@@ -499,6 +592,55 @@ int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int 
                                                        reinterpret_cast<const long long *>(keep),
                                                        reinterpret_cast<const long long *>(out_num), src, (int)top_k,
                                                        out_rows, reinterpret_cast<long long *>(out_index));
+    return (int)cudaGetLastError();
+}
+
+// ---- peer-memory plumbing (CUDA IPC) and cross-GPU completion flags -----------------------------------------------------
+int phnms_peer_alloc(size_t bytes, void **ptr, unsigned char *handle) {
+    if (!ptr || !handle || bytes == 0) return PHNMS_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PHNMS_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);   // a dedicated allocation: IPC handles name whole cudaMalloc allocations
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return (int)e;
+    }
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return PHNMS_OK;
+}
+
+int phnms_peer_open(const unsigned char *handle, void **ptr) {
+    if (!ptr || !handle) return PHNMS_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int phnms_peer_close(void *ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : PHNMS_ERR_BAD_ARG; }
+
+int phnms_peer_free(void *ptr) { return ptr ? (int)cudaFree(ptr) : PHNMS_ERR_BAD_ARG; }
+
+int phnms_peer_sync(uint64_t *const *signal_dst, const uint64_t *wait_src, int n, uint64_t signal_epoch,
+                    uint64_t wait_epoch, uint64_t timeout_ns, int *status, void *stream) {
+    if (n < 1 || n > PHNMS_MAX_DST) return PHNMS_ERR_BAD_ARG;
+    if ((signal_epoch && !signal_dst) || (wait_epoch && !wait_src)) return PHNMS_ERR_BAD_ARG;
+    if (!signal_epoch && !wait_epoch) return PHNMS_OK;
+    PeerSyncArgs a;
+    a.n = n;
+    a.signal_epoch = signal_epoch;
+    a.wait_epoch = wait_epoch;
+    a.timeout_ns = timeout_ns ? timeout_ns : 10000000000ull;
+    for (int d = 0; d < kMaxCollectDst; ++d)
+        a.signal_dst[d] = (signal_epoch && d < n) ? reinterpret_cast<unsigned long long *>(signal_dst[d]) : nullptr;
+    a.wait_src = reinterpret_cast<const unsigned long long *>(wait_src);
+    a.status = status;
+    phnms_peer_sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -78,7 +78,7 @@ def _workspace(L, dev, stream, F, N, n_off, t, tp):
     return ws, nbytes
 
 
-def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tune, keep, num, parent):
+def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tune, keep, num, parent, collect=None):
     top_k = int(top_k)
     if top_k < 0:
         raise TypeError("top_k must be non-negative (unsigned long in the reference, nms.cpp:48)")
@@ -93,9 +93,13 @@ def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tun
     try:
         stream = torch.cuda.current_stream(dev).cuda_stream
         ws, ws_bytes = _workspace(L, dev, stream, F, N, n_off, t, tp)
-        rc = L.phnms_forward_f32(boxes.data_ptr(), scores.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
-                                 F, N, n_off, float(overlap), top_k, int(sort_model), keep.data_ptr(), num.data_ptr(),
-                                 parent.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, tp, stream)
+        args = (boxes.data_ptr(), scores.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
+                F, N, n_off, float(overlap), top_k, int(sort_model), keep.data_ptr(), num.data_ptr(),
+                parent.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, tp, stream)
+        if collect is None:
+            rc = L.phnms_forward_f32(*args)
+        else:
+            rc = L.phnms_forward_collect_f32(*args, ctypes.byref(collect))
     finally:
         if switch:
             torch.cuda.set_device(prev)
@@ -118,12 +122,15 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model
 
 
 def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, n_valid: torch.Tensor | None = None, *,
-                sort_model: int = _capi.SORT_TORCH_CUDA, tuning=None, out=None):
+                sort_model: int = _capi.SORT_TORCH_CUDA, tuning=None, out=None, collect=None):
     """F independent `nms` calls in one launch.
 
     boxes [F, N, 5+n_off], scores [F, N], n_valid [F] int32 (optional: real proposals per frame, rest is padding).
     Returns (keep[F, N], num_to_keep[F], parent_object_index[F, N]); frame f equals
     `nms(boxes[f, :n_valid[f]], scores[f, :n_valid[f]], overlap, top_k)` padded with zeros to N.
+
+    collect: optional `_capi.Collect` (see `phnet_b200.peer`): the kernels additionally store the compact record
+    {keep[f, :top_k], num_to_keep[f]} of every frame into each listed buffer -- local tensors or other GPUs' memory.
     """
     boxes, scores = _check_inputs(boxes, scores, batched=True)
     F, N, P = boxes.shape
@@ -137,7 +144,7 @@ def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, n_val
         parent = torch.empty((F, N), dtype=torch.int64, device=dev)
     else:
         keep, num, parent = out
-    _launch(boxes, scores, n_valid, F, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent)
+    _launch(boxes, scores, n_valid, F, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent, collect)
     return keep, num, parent
 
 

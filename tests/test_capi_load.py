@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == set(_capi.EXPORTS), "include/phnms.h and the ctypes binding disagree"
     for s in syms:
         assert hasattr(L, s), f"libphnms.so does not export {s}"
-    assert L.phnms_abi_version() == 3
+    assert L.phnms_abi_version() == _capi.ABI_VERSION == 4
 
 
 def test_library_is_sm100a_only_and_has_tma_and_cluster_code():
@@ -61,6 +61,20 @@ def test_error_strings_and_argument_checks_without_a_gpu():
     assert L.phnms_forward_f32(nul, nul, nul, 0, 10, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == 0   # F == 0
     assert L.phnms_forward_f32(nul, nul, nul, 1, 10, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul) == -1  # null outputs
     assert L.phnms_order_f32(nul, nul, 1, 10, 0, nul, nul, 0, nul) == -1
+    # collection: descriptor checks (no destination, too many, top_k == 0, misaligned buffer) come before any CUDA call
+    args = (nul, nul, nul, 1, 10, 72, 50.0, 4, 0, nul, nul, nul, nul, 0, None, nul)
+    assert L.phnms_forward_collect_f32(*args, None) == -1
+    c = _capi.Collect()
+    c.n_dst = 0
+    assert L.phnms_forward_collect_f32(*args, ctypes.byref(c)) == -1
+    c.n_dst = _capi.MAX_DST + 1
+    assert L.phnms_forward_collect_f32(*args, ctypes.byref(c)) == -1
+    c = _capi.collect([4096])
+    assert L.phnms_forward_collect_f32(*(args[:7] + (0,) + args[8:]), ctypes.byref(c)) == -1       # top_k == 0
+    assert L.phnms_forward_collect_f32(*args, ctypes.byref(_capi.collect([4100]))) == -1            # not 8-byte aligned
+    assert L.phnms_peer_sync(None, nul, 0, 1, 1, 0, nul, nul) == -1
+    assert L.phnms_peer_sync(None, nul, 2, 0, 0, 0, nul, nul) == 0                                  # nothing to do
+    assert L.phnms_peer_open(None, None) == -1 and L.phnms_peer_close(None) == -1 and L.phnms_peer_free(None) == -1
     with pytest.raises(_capi.PhnmsError):
         _capi.check(-6)
 
