@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--max-clusters", type=int, default=0)
     ap.add_argument("--path", type=int, default=0)
-    ap.add_argument("--collect", default="peer", choices=["peer", "nccl"], help="N > 1: how the kept lanes are collected")
+    ap.add_argument("--collect", default="peer", choices=["peer", "nccl", "none"], help="N > 1: how the kept lanes are collected")
+    ap.add_argument("--lag", type=int, default=2, help="peer collection: a step waits for the records of step e - lag of all ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -233,12 +234,19 @@ def run_ours(a):
     # cannot be set up on this box: one NCCL all-gather per step on the compute stream (a side stream would take an SM
     # away from the persistent NMS kernel).
     collector, collection = None, "none (single GPU)"
-    if world > 1 and a.collect != "nccl":
+    lag = max(1, a.lag)
+    nbuf = 2 * lag + 3
+    mode = a.collect if world > 1 else "none"
+    if world > 1 and mode == "none":
+        collection = "none (diagnostic run: results stay on their rank)"
+    elif world > 1 and mode != "nccl":
         try:
             from phnet_b200 import peer
-            collector = peer.PeerCollector(F, a.top_k + 1, nbuf=3)
-            collection = "kernel stores into every rank's buffer over peer memory (CUDA IPC + NVLink), flag kernel per step"
+            collector = peer.PeerCollector(F, a.top_k + 1, nbuf=nbuf)
+            collection = (f"records stored into every rank's buffer over peer memory (CUDA IPC + NVLink) by the op itself; one flag "
+                          f"kernel per step signals this step and waits for step e-{lag} of all ranks ({nbuf} rotating buffers)")
         except Exception as e:   # noqa: BLE001 -- report why, fall back to the collective
+            mode = "nccl"
             collection = f"NCCL all_gather_into_tensor per step (peer memory unavailable: {type(e).__name__}: {e})"
     elif world > 1:
         collection = "NCCL all_gather_into_tensor per step (requested)"
@@ -252,17 +260,23 @@ def run_ours(a):
         if ev_pair is not None:
             ev_pair[0].record(cur)
         if collector is not None:
-            nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b], collect=collector.collect_arg(e % 3))
+            nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b], collect=collector.collect_arg(e % nbuf))
         else:
             nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b])
         if ev_pair is not None:
             ev_pair[1].record(cur)
         if collector is not None:
-            # records of step e are on their way to every rank; those of step e-1 are complete everywhere when this returns.
-            # (Buffer e % 3 is next written by step e + 3, which every rank launches after it has seen epoch e + 1 of all.)
-            collector._sync(e, e - 1, 10.0)
-            gathered[0] = collector.gathered((e - 1) % 3)
-        elif world > 1:
+            # Records of step e are on their way to every rank; those of step e-lag are complete everywhere when this
+            # returns (a consumer of the gathered results runs `lag` steps behind the producer, which absorbs the
+            # step-to-step jitter between GPUs).  A rank can run at most lag + 1 steps ahead of the slowest one (it waits
+            # for epoch e - lag of everybody) and a consumer reads records that are lag + 1 steps old, so 2 * lag + 3
+            # rotating buffers guarantee that nobody overwrites records a peer has yet to read.
+            collector._sync(e, max(e - lag, 0), 10.0)
+            if ev_pair is not None and len(ev_pair) > 2:
+                ev_pair[2].record(cur)
+            if e > lag:
+                gathered[0] = collector.gathered((e - lag) % nbuf)
+        elif mode == "nccl":
             packed = sharding.pack_kept(outs[b][0], outs[b][1], a.top_k)
             gathered[0] = sharding.gather_kept(packed, F * world)
 
@@ -274,25 +288,37 @@ def run_ours(a):
 
     for i in range(max(a.warmup, 3)):
         step(i)
-    fence()
-
-    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    pairs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(a.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    # Everything slow and rank-dependent happens BEFORE the barrier that opens the timed region: NVML initialisation is
+    # serialised across the processes of a box (measured: ranks entered the timed loop up to 12 ms apart when it sat
+    # after the barrier, which a lock-step collection then pays as idle time in every rank's clock).
+    clocks = ClockSampler(local)
+    fence()
+    with clocks:
         e0.record()
         for i in range(a.steps):
             step(i, pairs[i])
         e1.record()
         fence()
     ms_total = e0.elapsed_time(e1)
-    kern_ms = statistics.mean(p0.elapsed_time(p1) for p0, p1 in pairs)
+    kern_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in pairs)
+    sync_ms = statistics.mean(p[1].elapsed_time(p[2]) for p in pairs) if collector is not None else 0.0
+    gap_ms = statistics.mean(pairs[i][1].elapsed_time(pairs[i + 1][0]) for i in range(a.steps - 1)) if a.steps > 1 else 0.0
+    per_rank = None
+    if world > 1:
+        mine_t = torch.tensor([ms_total / a.steps, kern_ms, gap_ms, sync_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allr, mine_t)
+        per_rank = {"ms_per_step": [round(float(t[0]), 4) for t in allr], "op_ms": [round(float(t[1]), 4) for t in allr],
+                    "between_ops_ms": [round(float(t[2]), 4) for t in allr], "flag_kernel_ms": [round(float(t[3]), 4) for t in allr]}
     if collector is not None:
         # the last step's records: wait for them, then check the gathered buffer against this rank's own results
         collector.wait(step_no[0])
         torch.cuda.synchronize(dev)
         if collector.status() != 0:
             raise SystemExit(f"bench.py: peer collection timed out waiting for rank {collector.status() - 1}")
-        last = collector.gathered(step_no[0] % 3)
+        last = collector.gathered(step_no[0] % nbuf)
         mine = sharding.pack_kept(outs[(a.steps - 1) & 1][0], outs[(a.steps - 1) & 1][1], a.top_k)
         assert torch.equal(last[rank * F:(rank + 1) * F], mine), "collected records differ from this rank's keep / num"
         assert bool((last[:, a.top_k] >= 1).all()), "a rank's records are missing from the gathered buffer"
@@ -358,7 +384,7 @@ def run_ours(a):
                        "proposals": N, "offsets": n_off, "overlap": a.overlap, "top_k": a.top_k,
                        "l2": f"inputs are {F * N * (6 + n_off) * 4 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
                        "parallelism": f"frames sharded x{world}; no data-path collective; kept lanes collected on every rank once per step" if world > 1 else "single GPU",
-                       "collection": collection,
+                       "collection": collection, "per_rank": per_rank,
                        "plan": plan},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(N, n_off, F), "peak_source": peak_src,

@@ -34,8 +34,9 @@ class PeerCollector:
         c = pc.collect_arg(i % nbuf)            # pass to nms_batched(..., collect=c): rank r writes rows r*rows .. of all ranks
         pc.signal(epoch)                         # after the kernel: my records of this step are complete everywhere
         pc.wait(epoch)                           # before reading pc.gathered(i % nbuf): everyone's records have arrived
-    A buffer may be written again once every rank has finished reading it; signalling after the read and waiting for
-    epoch e before launching step e + nbuf - 1 (what `bench.py` does) guarantees that.
+    A buffer may be written again only when every rank has finished reading it.  With a consumer that runs `lag` steps
+    behind (wait for epoch e - lag at step e, as bench.py does) a rank is at most lag + 1 steps ahead of the slowest one,
+    so nbuf = 2 * lag + 3 rotating buffers are safe; with signal_and_wait every step (lock step), nbuf = 2 suffices.
     """
 
     def __init__(self, rows_per_rank: int, width: int, nbuf: int = 3, group=None, device=None):
