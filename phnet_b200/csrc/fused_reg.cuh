@@ -24,7 +24,7 @@ namespace phnms {
 constexpr int kCand = 4;   // candidates every CTA publishes per exchange (fallback batches)
 constexpr int kTopM = 16;  // capacity: per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch);
                            // FusedParams::topm_count (8 for top_k <= 4, else 16) of them are produced and fetched
-constexpr int kPlanLanes = 4;    // kept lanes of the planned batch evaluated per pass, one proposal per thread (n_off 72 / small frames)
+constexpr int kPlanLanes = 2;    // kept lanes of the planned batch evaluated per pass, one proposal per thread (n_off 72 / small frames)
 constexpr int kPlanLanes2 = 2;   // same, two proposals per thread (n_off 36): chains per thread = lanes x 2
 constexpr bool kSkipGroups = true;   // warp-uniform skip of 8-word groups outside the kept lane's own range
 constexpr bool kPackedSub = true;    // a - x of two neighbouring offsets as one FADD2 (sub.f32x2)
@@ -176,18 +176,26 @@ __device__ __forceinline__ Slab slab_geometry(const FusedParams &p, long long f,
 // one more bulk copy on the same mbarrier.
 __device__ __forceinline__ void request_slab(const FusedParams &p, long long f, const Slab &s, unsigned char *rows_buf,
                                              uint32_t bar, int tid, int T, int P, unsigned char *cand_dst,
-                                             uint32_t cand_bytes, float *sbuf) {
+                                             uint32_t cand_bytes, float *sbuf, bool sbulk) {
     const float *src = p.props + ((size_t)f * p.N + s.r0) * P;
     const bool body = s.total != 0u;
     const bool cand = p.topm != nullptr;
     float *rows = reinterpret_cast<float *>(rows_buf + 16 - s.head);
-    // this CTA's slice of the scores: asynchronous 4-byte copies (no register is tied up while they are in flight)
-    for (int c = tid; c < s.nloc; c += T) cp_async_4(smem_u32(sbuf + c), p.scores + (size_t)f * p.N + s.r0 + c);
-    cp_async_commit();
+    // this CTA's slice of the scores: one more bulk copy when it is 16-byte aligned (`sbulk`), else asynchronous 4-byte
+    // copies (no register is tied up while they are in flight)
+    const uint32_t sbytes = sbulk ? (((uint32_t)s.nloc * 4u + 15u) & ~15u) : 0u;
+    if (sbulk) {
+        if (tid == 64 && sbytes) bulk_g2s(smem_u32(sbuf), p.scores + (size_t)f * p.N + s.r0, sbytes, bar);
+    } else {
+        for (int c = tid; c < s.nloc; c += T) cp_async_4(smem_u32(sbuf + c), p.scores + (size_t)f * p.N + s.r0 + c);
+        cp_async_commit();
+    }
     if (cand) {
-        if (tid == 0) mbar_arrive_expect_tx(bar, s.total + cand_bytes);
+        if (tid == 0) mbar_arrive_expect_tx(bar, s.total + cand_bytes + sbytes);
         if (tid == 32)
             bulk_g2s(smem_u32(cand_dst), reinterpret_cast<const unsigned char *>(p.topm) + (size_t)f * cand_bytes, cand_bytes, bar);
+    } else if (sbytes && !body) {
+        if (tid == 0) mbar_arrive_expect_tx(bar, sbytes);
     }
     if (body) {
         // No proxy fence: the generic-proxy READS of the staging buffer are ordered before this async-proxy write by
@@ -195,7 +203,7 @@ __device__ __forceinline__ void request_slab(const FusedParams &p, long long f, 
         // streaming stores to HBM: 2.3k cycles per frame in the phase trace).  The copy is cut into up to 8 chunks,
         // each issued by lane 0 of a different warp (back-to-back UBLKCPs from one thread serialise on the TMA queue
         // and sat on the critical path); a chunk may complete before thread 0 has armed the barrier, which is fine.
-        if (tid == 0 && !cand) mbar_arrive_expect_tx(bar, s.total);
+        if (tid == 0 && !cand) mbar_arrive_expect_tx(bar, s.total + sbytes);
         {
             const int nw = T >> 5, issuers = slab_issuers(T);
             const int w = (tid >> 5), k = nw - 1 - w;   // last warps issue: warp 0 has the first-batch work ahead of it
@@ -520,11 +528,14 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         cluster_wait_acquire();
     }
 
-    uint32_t load_phase = 0, round_ctr = 0, fpar = 0, iter = 0;
+    uint32_t load_phase = 0, round_ctr = 0, iter = 0;
     int tcount = 0;
     (void)tcount;
     // slab geometry: identical for every frame in the common case (see Slab), then kept in shared memory
     const bool geo_uniform = slab_is_uniform(p, P);
+    // scores ride on the TMA as well when every CTA's slice of every frame is 16-byte aligned and a multiple of 16 bytes
+    // up to the end of the frame (T >= 96 so that thread 64 exists)
+    const bool sbulk = geo_uniform && ((((uintptr_t)p.scores) | (uintptr_t)(p.N * 4) | (uintptr_t)(p.rpc * 4)) & 15u) == 0u && T >= 96;
     const unsigned char *geo = smem + 64;
     if (geo_uniform && tid == 0) {
         const Slab s0 = slab_compute(p, 0, rank, P, T);
@@ -534,19 +545,20 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
     __syncthreads();
     if (f < p.F)
         request_slab(p, f, slab_geometry(p, f, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P, pslots,
-                     (uint32_t)(p.topm_count * SLOT), sbuf);
+                     (uint32_t)(p.topm_count * SLOT), sbuf, sbulk);
     // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
     // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
     const int lcap = min(T * CPT - p.rpc, 31);
 
     for (; f < p.F; f = f_next, ++iter) {
         PHNMS_TRACE(1);  // frame start
+        const uint32_t fpar = iter & 1u;   // parity of the double-buffered candidate block / scores
         if (dyn && csize > 1) cluster_arrive_relaxed();
         long long my_claim = 0;
         if (dyn && rank == 0 && tid == 0) my_claim = (long long)atomicAdd(p.claim_ctr, 1ull);   // frame of iteration iter + 2
         // ---- staging -> registers -------------------------------------------------------------------------------
         const Slab cur = slab_geometry(p, f, rank, P, T, geo_uniform, geo);
-        if (cur.total != 0u || p.topm != nullptr) {
+        if (cur.total != 0u || p.topm != nullptr || (sbulk && cur.nloc > 0)) {
             if (kTrace && p.trace_len < 0) mbar_wait_watch(bar_load, load_phase, p.trace, 1, f, round_ctr);
             else mbar_wait(bar_load, load_phase);
             load_phase ^= 1u;
@@ -622,7 +634,7 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         if (more)
             request_slab(p, f_next, slab_geometry(p, f_next, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P,
                          pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(p.topm_count * SLOT),
-                         sbuf + (fpar ^ 1u) * sbuf_stride);
+                         sbuf + (fpar ^ 1u) * sbuf_stride, sbulk);
         PHNMS_TRACE(4);  // next slab requested
         // hand the claimed frame index to the cluster; peers read it after the second barrier of their next frame
         // (sent here, mid-frame, so that it is long there when they need it)
@@ -655,19 +667,11 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         // column is touched: no selection, no exchange, no barrier -- the kept candidates are evaluated two per pass.
         if (p.topm != nullptr) {
             const unsigned char *csl = pslots + (size_t)fpar * kTopM * L.slot_stride;
-            const uint32_t aux = lane < kTopM ? reinterpret_cast<const uint32_t *>(csl + (size_t)lane * L.slot_stride)[7] : 0u;
-            const int nc = min((int)(__shfl_sync(0xffffffffu, aux, 0) & 0xffffu), p.topm_count);
-            uint32_t alive = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u), kept = 0u;
-            long long nk = 0;
-            for (int i = 0; i < nc; ++i) {
-                const uint32_t adj = __shfl_sync(0xffffffffu, aux, i) >> 16;
-                if ((alive >> i) & 1u) {
-                    kept |= 1u << i;
-                    alive &= ~adj;
-                    ++nk;
-                    if (nk == p.top_k) break;   // nms_kernel.cu:133
-                }
-            }
+            // aux of slot 0: number of valid candidates; aux of slot 1: the kept set of the greedy scan over the candidates,
+            // done once per frame by phnms_topm_kernel (which also stored their indices to keep[f, 0 ..], :118)
+            const int nc = min((int)(reinterpret_cast<const uint32_t *>(csl)[7] & 0xffffu), p.topm_count);
+            uint32_t kept = reinterpret_cast<const uint32_t *>(csl + L.slot_stride)[7] & 0xffffu;
+            if (nc < 2) kept = (uint32_t)nc;   // (a frame of one proposal has no valid slot 1)
             auto real_hdr = [&](int c) { return p.props + ((size_t)f * p.N + (uint32_t)myK[c]) * P; };
             while (kept) {
                 constexpr int NKP = CPT == 1 ? kPlanLanes : kPlanLanes2;
@@ -681,8 +685,6 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
                         ++cnt;
                     }
                     hh[k] = csl + (size_t)max(i, 0) * L.slot_stride;   // padding lanes point at a valid slot and are ignored
-                    if (i >= 0 && rank == 0 && tid == 0)                // :118
-                        p.keep[(size_t)f * p.N + n + k] = (long long)reinterpret_cast<const uint32_t *>(hh[k])[1];
                 }
                 if (NKP == 1) {
                     const unsigned char *const h1[1] = {hh[0]};
@@ -943,7 +945,6 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             if (rank == 0 && tid == 0) p.num_keep[f] = p.top_k < n ? p.top_k : n;  // :142
         }
         PHNMS_TRACE(13);  // outputs written
-        fpar ^= 1u;
 
     }
 

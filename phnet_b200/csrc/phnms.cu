@@ -493,7 +493,8 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
                     if (e2 != cudaSuccess) return (int)e2;
                 }
                 phnms_topm_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(
-                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, thresh, topm, claim_ctr);
+                    props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, thresh, topm, claim_ctr, top_k,
+                    reinterpret_cast<long long *>(keep));
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
                                                                     const int32_t *__restrict__ n_valid, long long F,
                                                                     int N, int n_off, int sort_model, int count, float thr,
                                                                     int *__restrict__ topm,
-                                                                    unsigned long long *__restrict__ claim_ctr) {
+                                                                    unsigned long long *__restrict__ claim_ctr,
+                                                                    long long top_k, long long *__restrict__ keep) {
     extern __shared__ __align__(16) unsigned char smem_topm[];
     __shared__ float bit_key[kTopmWarps][32];
     __shared__ int bit_val[kTopmWarps][32];
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
 
     // slot j of the frame's candidate block = {key, index, start, end, mask0, mask1, mask2, aux} + the proposal's row
     // padded to a multiple of 4 words -- byte for byte what the fused kernel keeps in shared memory, so that it can pull
-    // the whole block with one bulk copy.  aux of slot 0 = number of valid candidates.
+    // the whole block with one bulk copy.  aux = adjacency bits << 16 | number of valid candidates (slot 1: | the kept set
+    // of the planned greedy scan instead of the count).
     const int P = 5 + n_off, P4 = (P + 3) & ~3, slot_words = 8 + P4;
     int *blk = topm + (size_t)f * count * slot_words;
     const bool ok = lane < count && mine != kNone64;
@@ -182,7 +184,24 @@ __global__ void __launch_bounds__(kTopmWarps * 32) phnms_topm_kernel(const float
                 atomicOr(&adj[i], 1u << j);
         }
         __syncwarp();
-        if (lane < count) h1.w = (adj[lane] << 16) | (uint32_t)nfound;
+        // The greedy scan over the candidates (nms_collect, :111-136, restricted to them) is done here, once per frame:
+        // candidate i is kept iff no kept candidate before it suppresses it; the scan stops after top_k kept lanes (:133).
+        // Kept candidates are final -- they are the first kept lanes of the frame, in this order -- so their indices go
+        // straight to keep[f, 0 ..] (:118); the fused kernel gets the kept set as a bitmask in slot 1's aux word.
+        uint32_t alive = nfound >= 32 ? 0xffffffffu : ((1u << nfound) - 1u), kept = 0u;
+        {
+            long long nk = 0;
+            for (int i = 0; i < nfound; ++i) {
+                if ((alive >> i) & 1u) {
+                    kept |= 1u << i;
+                    alive &= ~adj[i];
+                    if (lane == i && keep) keep[(size_t)f * N + nk] = (long long)(uint32_t)mine;
+                    ++nk;
+                    if (nk == top_k) break;
+                }
+            }
+        }
+        if (lane < count) h1.w = (adj[lane] << 16) | (lane == 1 ? kept & 0xffffu : (uint32_t)nfound);
 #pragma unroll
         for (int j = 0; j < kTopM; ++j) {
             if (j >= count) break;
