@@ -116,6 +116,22 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                             int64_t *trace, int trace_len);
 
 /*
+ * predictions_to_pred for a whole clip: the tensor part of libs/models/Router4OLV2.py:363-404
+ * (hdr == 6) and RouterV4.py:349-392 (hdr == 7) for every kept lane -- start / end rounding, the "extend to the bottom"
+ * mask (OpenLane-V models), the -2 fills, selection of the points with x >= 0, the flip, the y rescale (VIL-100 models) --
+ * i.e. exactly the `points` array the reference hands to `Lane(points=...)` (libs/utils/lane.py:4-16; the spline inside
+ * Lane stays on the host).  One launch, no host sync.
+ *   rows     [T, K, hdr + n_off] fp32 device: out_rows of phnms_get_lanes_f32;  num [T] int64: its out_num
+ *   prior_ys [n_off] fp64 device: torch.linspace(1, 0, n_off) (fp32, Router4OLV2.py:61) widened to double
+ *   ori_img_h, cut_height: arguments of the reference call (used by the VIL-100 variant only, RouterV4.py:378)
+ *   points   [T, K, n_off, 2] fp64: (x, y) in `Lane.points` order, zero padded;  npoints [T, K] int32: number of points,
+ *            0 where the reference skips the lane (<= 1 point) or the slot is empty;  meta [T, K, 3] fp32: start_x, start_y, conf
+ */
+int phnms_decode_lanes_f32(const float *rows, const int64_t *num, int64_t T, int64_t K, int n_off, int hdr,
+                           const double *prior_ys, double ori_img_h, double cut_height, double *points, int32_t *npoints,
+                           float *meta, void *stream);
+
+/*
  * Lane NMS + collection of the kept lanes (the multi-GPU "final collection" of the kept-lane results, done with plain
  * stores over peer memory instead of a collective).  Same as phnms_forward_f32; in addition the compact record of frame f,
  *     int64[top_k + 1] = { keep[f, 0 .. top_k-1] zero padded, num_keep[f] },

@@ -109,4 +109,95 @@ __global__ void __launch_bounds__(128) phnms_gather_kernel(const float *__restri
     }
 }
 
+// ---- predictions_to_pred on the device ----------------------------------------------------
+// The tensor part of libs/models/Router4OLV2.py:363-404 (hdr == 6) and RouterV4.py:349-392 (hdr == 7) for every kept lane
+// of a clip: start / end rounding, the "extend to the bottom" mask, the -2 fill, selection of the points with x >= 0, the
+// flip, the y rescale -- everything up to the `Lane(points=...)` constructor, which (a scipy spline) stays on the host.
+// One warp per (frame, slot).  Python semantics reproduced: round() is round-half-even on the double of the fp32 value
+// (rint), slices with negative bounds wrap like Python's (`lane_xs[end + 1:]` with end + 1 < 0), and the mask is computed
+// from the row BEFORE the -2 fills.
+//   rows     [T, K, hdr + n_off] fp32: get_lanes output (length column(s) already rounded, Router4OL.py:470)
+//   num      [T] int64 kept lanes per frame
+//   prior_ys [n_off] fp64: `torch.linspace(1, 0, n_off)` as the model holds it (Router4OLV2.py:61), widened to double
+//   points   [T, K, n_off, 2] fp64: (x, y) of the lane's points in the order `Lane.points` has them (flipped), zero padded
+//   npoints  [T, K] int32: points of the lane; 0 where the reference `continue`s (<= 1 point) or the slot is empty
+//   meta     [T, K, 3] fp32: start_x, start_y, conf  (lane[3], lane[2], lane[1], the Lane metadata)
+__device__ __forceinline__ int py_slice_index(int i, int n) { return i < 0 ? max(n + i, 0) : min(i, n); }
+
+__global__ void __launch_bounds__(128) phnms_decode_kernel(const float *__restrict__ rows, const long long *__restrict__ num,
+                                                          int K, int hdr, int n_off, const double *__restrict__ prior_ys,
+                                                          double ori_img_h, double cut_height, double *__restrict__ points,
+                                                          int *__restrict__ npoints, float *__restrict__ meta,
+                                                          long long total) {
+    __shared__ float xs_s[4][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long slot = (long long)blockIdx.x * 4 + warp;
+    if (slot >= total) return;
+    const long long t = slot / K;
+    const int k = (int)(slot - t * K);
+    const int C = hdr + n_off, n_strips = n_off - 1;
+    const float *row = rows + (size_t)slot * C;
+    double *out = points + (size_t)slot * n_off * 2;
+    float *xs = xs_s[warp];
+    for (int i = lane; i < n_off; i += 32) {
+        xs[i] = row[hdr + i];
+        out[2 * i] = 0.0;
+        out[2 * i + 1] = 0.0;
+    }
+    __syncwarp();
+    if (k >= num[t]) {
+        if (lane == 0) npoints[slot] = 0;
+        if (lane < 3) meta[slot * 3 + lane] = 0.0f;
+        return;
+    }
+    // start = min(max(0, int(round(lane[2] * n_strips))), n_strips) [+ invalid_len]; end = min(start + length - 1, n_off - 1)
+    int start = (int)rint((double)row[2] * (double)n_strips);
+    start = min(max(0, start), n_strips);
+    if (hdr == 7) start += (int)rint((double)row[6]);
+    const int length = (int)rint((double)row[5]);
+    const int end = min(start + length - 1, n_off - 1);
+    const int fill_from = py_slice_index(end + 1, n_off);   // lane_xs[end + 1:] = -2
+    const int head_len = py_slice_index(start, n_off);       // lane_xs[:start]
+    int cnt_after[3];                                         // valid points with a larger index, per 32-chunk
+    bool valid[3];
+    uint32_t bal[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int i = lane + 32 * c;
+        bool v = false;
+        if (i < n_off) {
+            bool masked = i >= fill_from;
+            if (i < head_len) {
+                if (hdr == 7) {
+                    masked = true;                            // RouterV4.py:372 lane_xs[:start] = -2
+                } else {                                      // Router4OLV2.py:382-385: keep only the run of in-image x that reaches `start`
+                    bool run = true;
+                    for (int j = i; j < head_len; ++j) run = run && (xs[j] >= 0.0f) && (xs[j] <= 1.0f);
+                    masked = masked || !run;
+                }
+            }
+            v = !masked && xs[i] >= 0.0f;                     // lane_xs >= 0 (after the -2 fills)
+        }
+        valid[c] = v;
+        bal[c] = __ballot_sync(0xffffffffu, v);
+    }
+    const int tot = __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]);
+    cnt_after[2] = 0;
+    cnt_after[1] = __popc(bal[2]);
+    cnt_after[0] = __popc(bal[2]) + __popc(bal[1]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (valid[c]) {
+            const int i = lane + 32 * c;
+            const int pos = cnt_after[c] + __popc(bal[c] & ~((2u << lane) - 1u));   // flipped: larger indices come first
+            double y = prior_ys[i];
+            if (hdr == 7) y = (y * (ori_img_h - cut_height) + cut_height) / ori_img_h;  // RouterV4.py:378
+            out[2 * pos] = (double)xs[i];
+            out[2 * pos + 1] = y;
+        }
+    }
+    if (lane == 0) npoints[slot] = tot <= 1 ? 0 : tot;       // `if len(lane_xs) <= 1: continue`
+    if (lane < 3) meta[slot * 3 + lane] = row[3 - lane];     // start_x = lane[3], start_y = lane[2], conf = lane[1]
+}
+
 }  // namespace phnms

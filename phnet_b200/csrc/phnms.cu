@@ -596,6 +596,19 @@ int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int 
     return (int)cudaGetLastError();
 }
 
+int phnms_decode_lanes_f32(const float *rows, const int64_t *num, int64_t T, int64_t K, int n_off, int hdr,
+                           const double *prior_ys, double ori_img_h, double cut_height, double *points, int32_t *npoints,
+                           float *meta, void *stream) {
+    if (T < 0 || K < 0 || (hdr != 6 && hdr != 7) || n_off < 2 || n_off > 96) return PHNMS_ERR_BAD_ARG;
+    if (T == 0 || K == 0) return PHNMS_OK;
+    if (!rows || !num || !prior_ys || !points || !npoints || !meta || !(ori_img_h > 0.0)) return PHNMS_ERR_BAD_ARG;
+    const long long total = (long long)T * K;
+    phnms_decode_kernel<<<(unsigned)((total + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        rows, reinterpret_cast<const long long *>(num), (int)K, hdr, n_off, prior_ys, ori_img_h, cut_height, points, npoints,
+        meta, total);
+    return (int)cudaGetLastError();
+}
+
 // ---- peer-memory plumbing (CUDA IPC) and cross-GPU completion flags -----------------------------------------------------
 int phnms_peer_alloc(size_t bytes, void **ptr, unsigned char *handle) {
     if (!ptr || !handle || bytes == 0) return PHNMS_ERR_BAD_ARG;

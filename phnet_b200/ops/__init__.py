@@ -1,6 +1,6 @@
 """Mirror of PHNet `libs/ops/__init__.py:1-3`: `from phnet_b200.ops import nms`."""
 from .nms import nms, nms_batched, sort_order, plan
 from .pipeline import HostLaneNMS, nms_host
-from .get_lanes import get_lanes
+from .get_lanes import get_lanes, decode_lanes
 
-__all__ = ["nms", "nms_batched", "sort_order", "plan", "HostLaneNMS", "nms_host", "get_lanes"]
+__all__ = ["nms", "nms_batched", "sort_order", "plan", "HostLaneNMS", "nms_host", "get_lanes", "decode_lanes"]

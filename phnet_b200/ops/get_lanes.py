@@ -3,8 +3,9 @@
 Mirrors the tensor part of PHNet's `get_lanes` (libs/models/Router4OL.py:437-479, Router4OLV2.py:406-448,
 RouterV4.py:394-442) for a whole clip at once: confidence filter, column drop + pixel/strip scaling, lane NMS,
 `predictions[keep]`, rounding of the length column(s).  The reference runs this once per frame in Python with two host
-syncs; here T frames take four launches (prepare, top-M select, fused NMS, gather) and no sync.  The spline / `Lane`
-decode that follows in the reference (`predictions_to_pred`) stays on the host and is out of scope.
+syncs; here T frames take four launches (prepare, top-M select, fused NMS, gather) and no sync.  `decode_lanes` then does
+the tensor part of `predictions_to_pred` (the `points` of every `Lane`) in one more launch; only the scipy spline inside
+`Lane` (libs/utils/lane.py:4-16) stays on the host.
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ import torch
 
 from .. import _capi
 
-__all__ = ["get_lanes"]
+__all__ = ["get_lanes", "decode_lanes"]
 
 
 def get_lanes(output: torch.Tensor, conf_threshold: float, nms_thres: float, max_lanes: int, img_w: int = 768, *,
@@ -54,3 +55,41 @@ def get_lanes(output: torch.Tensor, conf_threshold: float, nms_thres: float, max
     _capi.check(rc)
     ws.record_stream(torch.cuda.current_stream(dev))
     return lanes, num, index, keep_inds.bool()
+
+
+def decode_lanes(lanes: torch.Tensor, num: torch.Tensor, ori_img_h: float = 1.0, cut_height: float = 0.0,
+                 prior_ys: torch.Tensor | None = None):
+    """`predictions_to_pred` for a whole clip on the device (libs/models/Router4OLV2.py:363-404 for 6 + n_off wide rows,
+    RouterV4.py:349-392 for 7 + n_off wide rows): the `points` arrays the reference hands to `Lane(points=...)`.
+
+    lanes [T, K, C], num [T]: what `get_lanes` returned.  prior_ys: the model's buffer (default: torch.linspace(1, 0, n_off)).
+    Returns (points[T, K, n_off, 2] float64, npoints[T, K] int32, meta[T, K, 3] float32 = start_x, start_y, conf);
+    lane k of frame t has points[t, k, :npoints[t, k]]; npoints == 0 where the reference drops the lane (<= 1 point)."""
+    if not lanes.is_cuda or lanes.dtype != torch.float32 or not lanes.is_contiguous() or lanes.dim() != 3:
+        raise RuntimeError("lanes must be a contiguous float32 CUDA tensor [T, K, hdr + n_off]")
+    T, K, C = lanes.shape
+    if C - 6 in (36, 72):
+        hdr = 6
+    elif C - 7 in (36, 72):
+        hdr = 7
+    else:
+        raise RuntimeError("rows must be 6 + n_off (OpenLane-V) or 7 + n_off (VIL-100) wide with n_off in {36, 72}")
+    n_off = C - hdr
+    dev = lanes.device
+    if num.device != dev or num.dtype != torch.int64 or num.shape != (T,):
+        raise RuntimeError("num must be an int64 tensor [T] on the same device")
+    if prior_ys is None:
+        prior_ys = torch.linspace(1, 0, steps=n_off, dtype=torch.float32)        # Router4OLV2.py:61
+    ys = prior_ys.to(device=dev, dtype=torch.float64).contiguous()               # `.double()`, Router4OLV2.py:368
+    if ys.numel() != n_off:
+        raise RuntimeError("prior_ys must have n_off entries")
+    points = torch.empty((T, K, n_off, 2), dtype=torch.float64, device=dev)
+    npoints = torch.empty((T, K), dtype=torch.int32, device=dev)
+    meta = torch.empty((T, K, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _capi.lib().phnms_decode_lanes_f32(lanes.data_ptr(), num.data_ptr(), T, K, n_off, hdr, ys.data_ptr(),
+                                                float(ori_img_h), float(cut_height), points.data_ptr(), npoints.data_ptr(),
+                                                meta.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _capi.check(rc)
+    ys.record_stream(torch.cuda.current_stream(dev))
+    return points, npoints, meta
