@@ -387,41 +387,94 @@ __device__ __forceinline__ void freg_eval_multi(const FusedParams &p, long long 
         return;
     }
     float dist[NK][CPT];
+    constexpr bool kSkip = kSkipGroups && CPT >= 2;
 #pragma unroll
     for (int k = 0; k < NK; ++k)
 #pragma unroll
         for (int c = 0; c < CPT; ++c) dist[k][c] = 0.0f;
+    if constexpr (kSkip) {
 #pragma unroll
-    for (int w = 0; w < MW; ++w) {
-        uint32_t m[NK][CPT];   // pair masks of this 32-word span
+        for (int w = 0; w < MW; ++w) {
+            uint32_t m[NK][CPT];   // pair masks of this 32-word span
+            uint32_t um[NK];       // the kept lanes' own masks, through REDUX: a uniform register, so the skips below are
+                                   // warp-uniform branches (no reconvergence code)
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            const uint32_t ma = *reinterpret_cast<const uint32_t *>(hdr[k] + 16 + 4 * w);
+            for (int k = 0; k < NK; ++k) {
+                const uint32_t ma = *reinterpret_cast<const uint32_t *>(hdr[k] + 16 + 4 * w);
+                um[k] = kSkip ? __reduce_or_sync(0xffffffffu, ma) : 0xffffffffu;
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) m[k][c] = ma & mb[c][w];
-        }
+                for (int c = 0; c < CPT; ++c) m[k][c] = ma & mb[c][w];
+            }
+            // groups of 8 row words (two LDS.128 of a kept row); a group outside kept lane k's own range adds nothing to any
+            // of its pairs (the pair mask is a subset of the lane's mask) and is skipped by the whole warp.  Only with two
+            // proposals per thread (four chains: measured +9 % at n_off 36); with one proposal per thread the branches cost
+            // more in exposed LDS latency than the skipped work saves (measured -13 % at n_off 72)
 #pragma unroll
-        for (int g = 8 * w; g < 8 * w + 8; ++g) {
-            if (g >= 1 && g < P4 / 4) {
+            for (int q = 4 * w; q < 4 * w + 4; ++q) {
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
-                    const float4 av = lds_v4(a_addr[k] + 16 * g);
-                    const float a4[4] = {av.x, av.y, av.z, av.w};
+                    if (kSkip && ((um[k] >> ((8 * q) & 31)) & 0xffu) == 0u) continue;
 #pragma unroll
-                    for (int u = 0; u < 4; u += 2) {
-                        const int i = 4 * g + u;
-                        const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
+                    for (int h = 0; h < 2; ++h) {
+                        const int g = 2 * q + h;
+                        if (g >= 1 && g < P4 / 4) {
+                            const float4 av = lds_v4(a_addr[k] + 16 * g);
+                            const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-                        for (int c = 0; c < CPT; ++c) {
-                            float t0 = 0.0f, t1 = 0.0f;
-                            if (v0 && v1) {
-                                fsub2(a4[u], a4[u + 1], x[c][v0 ? i - 5 : 0], x[c][v1 ? i - 4 : 0], t0, t1);
-                            } else {
-                                if (v0) t0 = __fsub_rn(a4[u], x[c][v0 ? i - 5 : 0]);
-                                if (v1) t1 = __fsub_rn(a4[u + 1], x[c][v1 ? i - 4 : 0]);
+                            for (int u = 0; u < 4; u += 2) {
+                                const int i = 4 * g + u;
+                                const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c) {
+                                    float t0 = 0.0f, t1 = 0.0f;
+                                    if (v0 && v1) {
+                                        fsub2(a4[u], a4[u + 1], x[c][v0 ? i - 5 : 0], x[c][v1 ? i - 4 : 0], t0, t1);
+                                    } else {
+                                        if (v0) t0 = __fsub_rn(a4[u], x[c][v0 ? i - 5 : 0]);
+                                        if (v1) t1 = __fsub_rn(a4[u + 1], x[c][v1 ? i - 4 : 0]);
+                                    }
+                                    if (v0 && (m[k][c] & (1u << (i & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t0));
+                                    if (v1 && (m[k][c] & (1u << ((i + 1) & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t1));
+                                }
                             }
-                            if (v0 && (m[k][c] & (1u << (i & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t0));
-                            if (v1 && (m[k][c] & (1u << ((i + 1) & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t1));
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < MW; ++w) {
+            uint32_t m[NK][CPT];   // pair masks of this 32-word span
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const uint32_t ma = *reinterpret_cast<const uint32_t *>(hdr[k] + 16 + 4 * w);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) m[k][c] = ma & mb[c][w];
+            }
+#pragma unroll
+            for (int g = 8 * w; g < 8 * w + 8; ++g) {
+                if (g >= 1 && g < P4 / 4) {
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const float4 av = lds_v4(a_addr[k] + 16 * g);
+                        const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u += 2) {
+                            const int i = 4 * g + u;
+                            const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                float t0 = 0.0f, t1 = 0.0f;
+                                if (v0 && v1) {
+                                    fsub2(a4[u], a4[u + 1], x[c][v0 ? i - 5 : 0], x[c][v1 ? i - 4 : 0], t0, t1);
+                                } else {
+                                    if (v0) t0 = __fsub_rn(a4[u], x[c][v0 ? i - 5 : 0]);
+                                    if (v1) t1 = __fsub_rn(a4[u + 1], x[c][v1 ? i - 4 : 0]);
+                                }
+                                if (v0 && (m[k][c] & (1u << (i & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t0));
+                                if (v1 && (m[k][c] & (1u << ((i + 1) & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t1));
+                            }
                         }
                     }
                 }
