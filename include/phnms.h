@@ -116,6 +116,16 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                             int64_t *trace, int trace_len);
 
 /*
+ * The training-side line IoU: libs/utils/dynamic_assign.py:5-36
+ * `line_iou(pred, target, img_w, length=15, aligned)`.  pred [num_pred, n_off], target [num_target, n_off] fp32 device, x in
+ * pixels.  aligned != 0: num_pred == num_target, out [num_pred] = IoU of pair i (the LIoU loss term); aligned == 0:
+ * out [num_pred, num_target] = the pairwise matrix the dynamic-k assignment consumes (:83-125).  fp32, within 1e-5 relative of
+ * the reference (torch's reduction order over the offsets is not sequential).
+ */
+int phnms_line_iou_f32(const float *pred, const float *target, int64_t num_pred, int64_t num_target, int n_off, float img_w,
+                       float length, int aligned, float *out, void *stream);
+
+/*
  * predictions_to_pred for a whole clip: the tensor part of libs/models/Router4OLV2.py:363-404
  * (hdr == 6) and RouterV4.py:349-392 (hdr == 7) for every kept lane -- start / end rounding, the "extend to the bottom"
  * mask (OpenLane-V models), the -2 fills, selection of the points with x >= 0, the flip, the y rescale (VIL-100 models) --

@@ -109,6 +109,67 @@ __global__ void __launch_bounds__(128) phnms_gather_kernel(const float *__restri
     }
 }
 
+// ---- the training-side line IoU -----------------------------------------------------------
+// libs/utils/dynamic_assign.py:5-36 `line_iou(pred, target, img_w, length, aligned)`: every x offset is widened to a
+// segment of radius `length`; IoU = sum of per-offset overlaps / (sum of per-offset unions + 1e-9), offsets whose target is
+// outside [0, img_w) contributing nothing.  aligned: pair i of two equally long lists; otherwise the full
+// [num_pred, num_target] matrix the dynamic-k assignment consumes (:83-125).  fp32 throughout like the reference; the
+// sums run in ascending offset order (torch's vectorised reduction order differs: parity is to 1e-5 relative, stated in
+// the test).  torch.min / torch.max propagate NaN, fminf / fmaxf do not: emulated.
+__device__ __forceinline__ float tmin(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
+__device__ __forceinline__ float tmax(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+__global__ void __launch_bounds__(128) phnms_line_iou_kernel(const float *__restrict__ pred, const float *__restrict__ target,
+                                                            int num_pred, int num_target, int n_off, float img_w,
+                                                            float length, int aligned, float *__restrict__ out) {
+    extern __shared__ float liou_smem[];                 // [128][n_off + 1] pred tile, then [tile_t][n_off] targets
+    const int pitch = n_off + 1;
+    float *ps = liou_smem;
+    float *ts = liou_smem + 128 * pitch;
+    const int p0 = blockIdx.x * 128, tid = threadIdx.x;
+    const int np = min(128, num_pred - p0);
+    for (int i = tid; i < np * n_off; i += 128) ps[(i / n_off) * pitch + (i % n_off)] = pred[(size_t)p0 * n_off + i];
+    if (aligned) {
+        __syncthreads();
+        if (tid < np) {
+            const float *t = target + (size_t)(p0 + tid) * n_off;
+            float so = 0.0f, su = 0.0f;
+            for (int i = 0; i < n_off; ++i) {
+                const float pv = ps[tid * pitch + i], tv = t[i];
+                const float px1 = __fsub_rn(pv, length), px2 = __fadd_rn(pv, length);
+                const float tx1 = __fsub_rn(tv, length), tx2 = __fadd_rn(tv, length);
+                const bool invalid = (tv < 0.0f) || (tv >= img_w);
+                const float o = __fsub_rn(tmin(px2, tx2), tmax(px1, tx1)), u = __fsub_rn(tmax(px2, tx2), tmin(px1, tx1));
+                so = __fadd_rn(so, invalid ? 0.0f : o);
+                su = __fadd_rn(su, invalid ? 0.0f : u);
+            }
+            out[p0 + tid] = __fdiv_rn(so, __fadd_rn(su, 1e-9f));
+        }
+        return;
+    }
+    for (int t0 = 0; t0 < num_target; t0 += 32) {          // targets in tiles of 32 (a frame has a handful of lanes)
+        const int nt = min(32, num_target - t0);
+        __syncthreads();
+        for (int i = tid; i < nt * n_off; i += 128) ts[i] = target[(size_t)t0 * n_off + i];
+        __syncthreads();
+        if (tid < np) {
+            for (int t = 0; t < nt; ++t) {
+                float so = 0.0f, su = 0.0f;
+                for (int i = 0; i < n_off; ++i) {
+                    const float pv = ps[tid * pitch + i], tv = ts[t * n_off + i];
+                    const float px1 = __fsub_rn(pv, length), px2 = __fadd_rn(pv, length);
+                    const float tx1 = __fsub_rn(tv, length), tx2 = __fadd_rn(tv, length);
+                    const bool invalid = (tv < 0.0f) || (tv >= img_w);
+                    const float o = __fsub_rn(tmin(px2, tx2), tmax(px1, tx1)), u = __fsub_rn(tmax(px2, tx2), tmin(px1, tx1));
+                    so = __fadd_rn(so, invalid ? 0.0f : o);
+                    su = __fadd_rn(su, invalid ? 0.0f : u);
+                }
+                out[(size_t)(p0 + tid) * num_target + t0 + t] = __fdiv_rn(so, __fadd_rn(su, 1e-9f));
+            }
+        }
+    }
+}
+
 // ---- predictions_to_pred on the device ----------------------------------------------------
 // The tensor part of libs/models/Router4OLV2.py:363-404 (hdr == 6) and RouterV4.py:349-392 (hdr == 7) for every kept lane
 // of a clip: start / end rounding, the "extend to the bottom" mask, the -2 fill, selection of the points with x >= 0, the

@@ -596,6 +596,22 @@ int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int 
     return (int)cudaGetLastError();
 }
 
+int phnms_line_iou_f32(const float *pred, const float *target, int64_t num_pred, int64_t num_target, int n_off, float img_w,
+                       float length, int aligned, float *out, void *stream) {
+    if (num_pred < 0 || num_target < 0 || n_off < 1 || n_off > 250 || (aligned && num_pred != num_target))
+        return PHNMS_ERR_BAD_ARG;
+    if (num_pred == 0 || num_target == 0) return PHNMS_OK;
+    if (!pred || !target || !out) return PHNMS_ERR_BAD_ARG;
+    const size_t smem = (size_t)(128 * (n_off + 1) + 32 * n_off) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(phnms_line_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    phnms_line_iou_kernel<<<(unsigned)((num_pred + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
+        pred, target, (int)num_pred, (int)num_target, n_off, img_w, length, aligned, out);
+    return (int)cudaGetLastError();
+}
+
 int phnms_decode_lanes_f32(const float *rows, const int64_t *num, int64_t T, int64_t K, int n_off, int hdr,
                            const double *prior_ys, double ori_img_h, double cut_height, double *points, int32_t *npoints,
                            float *meta, void *stream) {

@@ -2,5 +2,6 @@
 from .nms import nms, nms_batched, sort_order, plan
 from .pipeline import HostLaneNMS, nms_host
 from .get_lanes import get_lanes, decode_lanes
+from .line_iou import line_iou
 
-__all__ = ["nms", "nms_batched", "sort_order", "plan", "HostLaneNMS", "nms_host", "get_lanes", "decode_lanes"]
+__all__ = ["nms", "nms_batched", "sort_order", "plan", "HostLaneNMS", "nms_host", "get_lanes", "decode_lanes", "line_iou"]
