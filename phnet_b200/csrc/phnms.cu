@@ -72,20 +72,21 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
         const bool reg_ok = (n_off == 36 || n_off == 72) && t.variant != PHNMS_FUSED_SMEM;
         if (reg_ok) {
             const int max_cpt = (n_off == 36) ? 2 : 1;
-            // A CTA wants >= 8 "spare lanes" beyond its rows: they hold the batch's candidates (fused_reg.cuh), without
-            // them every round after the first costs a cluster exchange.  Prefer the smallest cluster that leaves room.
+            // The smallest cluster whose CTAs can hold their share of the frame.  Threads: one (n_off 72) or two (n_off 36)
+            // proposals each, rounded up to a warp.  A CTA likes >= 8 "spare lanes" beyond its rows (they hold register
+            // copies of a fallback batch's candidates, fused_reg.cuh) -- but never at the price of a register-file
+            // occupancy step: 128 registers/thread give 4 / 3 / 2 / 1 CTAs per SM at <= 128 / 160 / 256 / 512 threads,
+            // and one more warp for the spares at 256 rows halves the resident rows per SM (measured: N = 256: 34 -> 54 M
+            // frames/s, N = 512: 18 -> 28 M, N = 2048: 3.4 -> 5.5 M, N = 4096: 1.4 -> 2.3 M without them).
             const int kSpare = 8;
             int csize = 0;
-            for (int pass = 0; pass < 2 && !csize; ++pass) {
-                const int need = pass == 0 ? kSpare : 0;
-                for (int i = 0; i < 5 && !csize; ++i) {
-                    const int c = cand[i];
-                    if (t.cluster && c != t.cluster) continue;
-                    const int rpc = rows_for(c);
-                    if (rpc + need > 512 * max_cpt) continue;
-                    if (freg_layout(rpc, P, c).total > smem_max) continue;
-                    csize = c;
-                }
+            for (int i = 0; i < 5 && !csize; ++i) {
+                const int c = cand[i];
+                if (t.cluster && c != t.cluster) continue;
+                const int rpc = rows_for(c);
+                if (rpc > 512 * max_cpt) continue;
+                if (freg_layout(rpc, P, c).total > smem_max) continue;
+                csize = c;
             }
             if (csize) {
                 const int rpc = rows_for(csize);
@@ -96,13 +97,14 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
                     cpt = (rpc + threads - 1) / threads;
                     if (cpt > max_cpt) return PHNMS_ERR_TUNING;
                 } else {
-                    // two proposals per thread where the registers allow it (n_off 36): better ILP, shared `a` loads
                     cpt = max_cpt;
-                    threads = round_up((rpc + kSpare + cpt - 1) / cpt, 32);
+                    threads = round_up((rpc + cpt - 1) / cpt, 32);
                     if (threads > 512) threads = 512;
                     if (threads < 128) threads = 128;
                     if (threads * cpt < rpc) return PHNMS_ERR_TUNING;
-                    if (threads >= rpc + kSpare) cpt = 1;
+                    if (threads >= rpc) cpt = 1;   // one proposal per thread already covers the rows
+                    if (threads * cpt - rpc < kSpare && threads + 32 <= 512 && 512 / (threads + 32) == 512 / threads)
+                        threads += 32;             // a warp of spare lanes where it costs no occupancy
                 }
                 const FregLayout L = freg_layout(rpc, P, csize);
                 int per_sm = smem_max / (L.total + 1024);

@@ -33,13 +33,15 @@ for N, n_off, top_k, F in shapes:
     if os.environ.get("SEARCH"):
         best = None
         for c in (1, 2, 4, 8, 16):
-            for t in (128, 256, 384, 512):
+            for t in (128, 160, 192, 224, 256, 288, 320, 384, 448, 512):
                 try:
                     tune = _capi.tuning(path=1, cluster=c, threads=t, variant=2)
                     _capi.plan(F, N, n_off, tune)
                 except Exception:
                     continue
                 m = timeit(props, scores, top_k, tune, out, reps=4)
+                if os.environ.get("SEARCH") == "2":
+                    print("   ", c, t, round(F / m / 1e3, 3), flush=True)
                 if best is None or m < best[0]:
                     best = (m, c, t)
         rec["best"] = {"cluster": best[1], "threads": best[2], "Mframes_s": round(F / best[0] / 1e3, 3), "frac": round(F * bpf / best[0] / 1e6 / 6554.2, 4)}

@@ -20,7 +20,7 @@ def run_both(props, scores, thr, top_k, dev, n_valid=None, tuning=None, sort_mod
 
 
 @pytest.mark.parametrize("n_off", [72, 36])
-@pytest.mark.parametrize("N", [1, 2, 7, 31, 32, 33, 64, 65, 100, 128, 129, 240, 500, 1000])
+@pytest.mark.parametrize("N", [1, 2, 7, 31, 32, 33, 64, 65, 100, 128, 129, 240, 256, 500, 512, 1000, 1024, 2048])
 def test_fused_auto_shapes(cuda_device, N, n_off):
     props, scores = synth.make_frames(6, N, n_off, seed=N * 7 + n_off)
     for top_k in (4, 8):
