@@ -116,6 +116,18 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                             int64_t *trace, int trace_len);
 
 /*
+ * Double precision boxes.  The reference instantiates its kernels for double as well (AT_DISPATCH_FLOATING_TYPES,
+ * libs/ops/csrc/nms_kernel.cu:171); PHNet itself never passes doubles, so this is a compatibility path (bitmask + scan,
+ * not the fused kernels).  The ordering is the caller's: `order` [F, N] int64 is what `scores.sort(0, True)` returned
+ * (libs/ops/csrc/nms.cpp:51) -- the Python mirror calls torch for it exactly like the reference does, so ties fall as they
+ * do there by construction.  props [F, N, 5 + n_off] fp64; the other arguments as in phnms_forward_f32.
+ */
+size_t phnms_ordered_f64_workspace_bytes(int64_t F, int64_t N);
+int phnms_forward_ordered_f64(const double *props, const int64_t *order, const int32_t *n_valid /* nullable */, int64_t F,
+                              int64_t N, int n_off, float thresh, int64_t top_k, int64_t *keep, int64_t *num_keep,
+                              int64_t *parent, void *ws, size_t ws_bytes, void *stream);
+
+/*
  * The training-side line IoU: libs/utils/dynamic_assign.py:5-36
  * `line_iou(pred, target, img_w, length=15, aligned)`.  pred [num_pred, n_off], target [num_target, n_off] fp32 device, x in
  * pixels.  aligned != 0: num_pred == num_target, out [num_pred] = IoU of pair i (the LIoU loss term); aligned == 0:

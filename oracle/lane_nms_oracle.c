@@ -285,6 +285,71 @@ int phoracle_nms_lazy(const float *props, const int64_t *idx, int64_t n, int n_o
     return 0;
 }
 
+/* ---- double precision boxes: nms_kernel<double> / devIoU<double> (nms_kernel.cu:26-48,171) ------------------------------
+ * Arithmetic as the reference's double instantiation compiles (SASS of oracle/_ref): the start is ONE fused multiply-add
+ * (nvcc contracts `a[2] * N_STRIPS + 0.5` under its default -fmad=true: DFMA), the end a chain of fp64 adds, both through
+ * F2I.F64.TRUNC; fp64 sequential distance; the limit is the FP32 product threshold * len (devIoU takes `const float
+ * threshold`) widened to double.  The ordering `idx` is given (the reference gets it from torch, nms.cpp:51). */
+static int32_t lane_start_f64(const double *row, int n_off) {
+    return cvt_rzi_s32_f64(fma(row[2], (double)(n_off - 1), 0.5));
+}
+static int32_t lane_end_f64(const double *row, int32_t start) {
+    double e = (((double)start + row[4]) - 1.0) + 0.5;
+    e = e - (double)(((row[4] - 1.0) < 0.0) ? 1 : 0);
+    return cvt_rzi_s32_f64(e);
+}
+static int pred_f64(const double *a, const double *b, int32_t sa, int32_t ea, int32_t sb, int32_t eb, int n_off,
+                    float threshold) {
+    const int32_t start = sa > sb ? sa : sb;
+    int32_t end = ea < eb ? ea : eb;
+    if (end > n_off - 1) end = n_off - 1;
+    if (end < start) return 0;
+    double dist = 0.0;
+    uint8_t i = (uint8_t)((uint32_t)start + 5u);
+    const int32_t last = wrap_add(end, 5);
+    for (; (int32_t)i <= last; ++i) {
+        if (a[i] < b[i]) dist += b[i] - a[i];
+        else dist += a[i] - b[i];
+    }
+    const float lim = threshold * (float)wrap_add(wrap_sub(end, start), 1);
+    return dist < (double)lim;
+}
+int phoracle_nms_ordered_f64(const double *props, const int64_t *idx, int64_t n, int n_off, float thr, int64_t top_k,
+                             int64_t *keep, int64_t *num_to_keep, int64_t *parent) {
+    const int64_t P = 5 + n_off;
+    if (n_off < 1 || n_off > 250) return -1;
+    if ((n + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK >= MAX_COL_BLOCKS) return -1;
+    if (n == 0) { *num_to_keep = 0; return 0; }
+    uint8_t *removed = (uint8_t *)calloc((size_t)n, 1);
+    int32_t *se = (int32_t *)malloc((size_t)n * 2 * sizeof(int32_t));
+    for (int64_t r = 0; r < n; ++r) {
+        se[2 * r] = lane_start_f64(props + r * P, n_off);
+        se[2 * r + 1] = lane_end_f64(props + r * P, se[2 * r]);
+    }
+    int64_t nk = 0;
+    for (int64_t i = 0; i < n; ++i) parent[i] = 0;
+    for (int64_t i = 0; i < n; ++i) {          /* the rows nms_collect reads (:116-129), see phoracle_nms_lazy */
+        if (removed[i]) continue;
+        keep[nk] = idx[i];
+        const int64_t ra = idx[i];
+        for (int64_t j = i + 1; j < n; ++j) {
+            const int64_t rb = idx[j];
+            if (pred_f64(props + ra * P, props + rb * P, se[2 * ra], se[2 * ra + 1], se[2 * rb], se[2 * rb + 1], n_off, thr)) {
+                removed[j] = 1;
+                parent[idx[j]] = nk + 1;
+            }
+        }
+        parent[idx[i]] = nk + 1;
+        nk++;
+        if (nk == top_k) break;
+    }
+    for (int64_t i = nk; i < n; ++i) keep[i] = 0;
+    *num_to_keep = top_k < nk ? top_k : nk;
+    free(removed);
+    free(se);
+    return 0;
+}
+
 /* ---- whole op on one frame: sort model + NMS ---------------------------------------------- */
 int phoracle_nms(const float *props, const float *scores, int64_t n, int n_off, float thr,
                  int64_t top_k, int sort_model, int lazy, int64_t *keep, int64_t *num_to_keep,

@@ -63,6 +63,9 @@ def lib():
                                            ctypes.c_int, _i64p, _i64p, _i64p]
         L.phoracle_nms_batched.restype = ctypes.c_int
         L.phoracle_max_threads.restype = ctypes.c_int
+        L.phoracle_nms_ordered_f64.argtypes = [ctypes.POINTER(ctypes.c_double), _i64p, ctypes.c_int64, ctypes.c_int,
+                                               ctypes.c_float, ctypes.c_int64, _i64p, _i64p, _i64p]
+        L.phoracle_nms_ordered_f64.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -73,6 +76,22 @@ def _f32(x):
 
 def _ptr(a, t):
     return a.ctypes.data_as(t)
+
+
+def nms_f64(props, idx, thr: float, top_k: int):
+    """One frame of DOUBLE boxes with a given ordering `idx` (what `scores.sort(0, True)` returned, nms.cpp:51):
+    nms_kernel<double> + nms_collect.  Returns (keep[N] i64, num_to_keep int, parent[N] i64)."""
+    p = np.ascontiguousarray(np.asarray(props, dtype=np.float64))
+    n, P = p.shape
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    keep = np.zeros(n, dtype=np.int64)
+    parent = np.zeros(n, dtype=np.int64)
+    num = np.zeros(1, dtype=np.int64)
+    rc = lib().phoracle_nms_ordered_f64(p.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _ptr(idx, _i64p), n, P - 5, thr,
+                                        top_k, _ptr(keep, _i64p), _ptr(num, _i64p), _ptr(parent, _i64p))
+    if rc != 0:
+        raise RuntimeError("oracle: bad argument")
+    return keep, int(num[0]), parent
 
 
 def max_threads() -> int:

@@ -598,6 +598,48 @@ int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int 
     return (int)cudaGetLastError();
 }
 
+size_t phnms_ordered_f64_workspace_bytes(int64_t F, int64_t N) {
+    if (F < 0 || N < 0) return 0;
+    return (size_t)F * N * (size_t)((N + 63) / 64) * 8 + 256;
+}
+
+int phnms_forward_ordered_f64(const double *props, const int64_t *order, const int32_t *n_valid, int64_t F, int64_t N,
+                              int n_off, float thresh, int64_t top_k, int64_t *keep, int64_t *num_keep, int64_t *parent,
+                              void *ws, size_t ws_bytes, void *stream_) {
+    int rc = check_shape(F, N, n_off);
+    if (rc != PHNMS_OK) return rc;
+    if (top_k < 0) return PHNMS_ERR_BAD_ARG;
+    if (F == 0) return PHNMS_OK;
+    if (!num_keep) return PHNMS_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N == 0) return (int)cudaMemsetAsync(num_keep, 0, (size_t)F * 8, stream);
+    if (!props || !order || !keep || !parent) return PHNMS_ERR_BAD_ARG;
+    if (((uintptr_t)props | (uintptr_t)order | (uintptr_t)keep | (uintptr_t)parent | (uintptr_t)num_keep) & 7u)
+        return PHNMS_ERR_BAD_ARG;
+    if (!ws || ws_bytes < phnms_ordered_f64_workspace_bytes(F, N)) return PHNMS_ERR_WORKSPACE;
+    DeviceInfo dev;
+    rc = device_info(&dev);
+    if (rc != 0) return rc;
+    if (dev.cc_major != 10) return PHNMS_ERR_DEVICE;
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const int col_blocks = (int)((N + 63) / 64);
+    const long long *ord = reinterpret_cast<const long long *>(order);
+    for (int64_t f0 = 0; f0 < F; f0 += 65535) {            // gridDim.z is limited to 65535 frames per launch
+        const int64_t fc = (F - f0) < 65535 ? (F - f0) : 65535;
+        dim3 grid((unsigned)((N + 127) / 128), (unsigned)col_blocks, (unsigned)fc);
+        phnms_mask_f64_kernel<<<grid, 128, 0, stream>>>(props + (size_t)f0 * N * (5 + n_off), ord + (size_t)f0 * N,
+                                                        n_valid ? n_valid + f0 : nullptr, (int)N, n_off, thresh,
+                                                        col_blocks, mask + (size_t)f0 * N * col_blocks);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    phnms_scan_kernel<<<(unsigned)F, 32, 0, stream>>>(ord, mask, n_valid, (int)N, col_blocks, top_k,
+                                                      reinterpret_cast<long long *>(keep),
+                                                      reinterpret_cast<long long *>(num_keep),
+                                                      reinterpret_cast<long long *>(parent));
+    return (int)cudaGetLastError();
+}
+
 int phnms_line_iou_f32(const float *pred, const float *target, int64_t num_pred, int64_t num_target, int n_off, float img_w,
                        float length, int aligned, float *out, void *stream) {
     if (num_pred < 0 || num_target < 0 || n_off < 1 || n_off > 250 || (aligned && num_pred != num_target))

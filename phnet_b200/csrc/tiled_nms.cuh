@@ -307,4 +307,59 @@ __global__ void __launch_bounds__(32) phnms_scan_kernel(const long long *__restr
     if (lane == 0) num_keep[f] = top_k < nk ? top_k : nk;            // :142
 }
 
+// ---- double precision boxes (the reference also instantiates nms_kernel<double>, nms_kernel.cu:171) --------------------
+// A compatibility path, not a fast one: one thread per (sorted row, column block) evaluates its 64 pairs with scalar
+// loops straight from global memory; phnms_scan_kernel then runs unchanged on the bitmask.  The arithmetic follows the
+// SASS of the reference's double instantiation (oracle/_ref): the start is ONE fused multiply-add
+// (`a[2] * N_STRIPS + 0.5` contracts to DFMA under nvcc's default -fmad=true), the end is a chain of DADDs, both through
+// F2I.F64.TRUNC; the distance is a sequential fp64 sum; the limit is the FP32 product thr * len widened to double
+// (devIoU takes `const float threshold`, :26).
+__device__ __forceinline__ int lane_start_f64(double y, int n_off) {
+    return __double2int_rz(__fma_rn(y, (double)(n_off - 1), 0.5));                          // :29-30
+}
+__device__ __forceinline__ int lane_end_f64(double len, int start) {                         // :32-33
+    double e = __dadd_rn(__dadd_rn(__dadd_rn((double)start, len), -1.0), 0.5);
+    e = __dsub_rn(e, (__dadd_rn(len, -1.0) < 0.0) ? 1.0 : 0.0);
+    return __double2int_rz(e);
+}
+__device__ __forceinline__ bool pair_hit_f64(const double *a, const double *b, int sa, int ea, int sb, int eb, int n_off,
+                                             float thr) {
+    const int start = max(sa, sb);                                                           // :31
+    const int end = min(min(ea, eb), n_off - 1);                                             // :34
+    if (end < start) return false;                                                           // :36
+    const int i0 = (int)(((uint32_t)start + 5u) & 255u);                                     // :38 unsigned char counter
+    const int last = (int)((uint32_t)end + 5u);
+    double dist = 0.0;
+    for (int i = i0; i <= last; ++i) {
+        const double av = a[i], bv = b[i];
+        dist = __dadd_rn(dist, (av < bv) ? __dsub_rn(bv, av) : __dsub_rn(av, bv));           // :39-43
+    }
+    const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
+    return dist < (double)__fmul_rn(thr, (float)len);                                        // :46
+}
+
+__global__ void __launch_bounds__(128) phnms_mask_f64_kernel(const double *__restrict__ props,
+                                                            const long long *__restrict__ order,
+                                                            const int32_t *__restrict__ n_valid, int N, int n_off,
+                                                            float thr, int col_blocks,
+                                                            unsigned long long *__restrict__ mask) {
+    const long long f = blockIdx.z;
+    const int w = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x, P = 5 + n_off;
+    int n = N;
+    if (n_valid) n = max(0, min(n_valid[f], N));
+    if (i >= n || w < (i >> 6)) return;                                                      // :56 upper triangle only
+    const long long *ord = order + (size_t)f * N;
+    const double *a = props + ((size_t)f * N + ord[i]) * P;
+    const int sa = lane_start_f64(a[2], n_off), ea = lane_end_f64(a[4], sa);
+    unsigned long long bits = 0ull;
+    for (int b = 0; b < 64; ++b) {
+        const int j = 64 * w + b;
+        if (j <= i || j >= n) continue;                                                      // :85-87 strict upper triangle
+        const double *q = props + ((size_t)f * N + ord[j]) * P;
+        const int sb = lane_start_f64(q[2], n_off), eb = lane_end_f64(q[4], sb);
+        if (pair_hit_f64(a, q, sa, ea, sb, eb, n_off, thr)) bits |= 1ull << b;
+    }
+    mask[((size_t)f * N + i) * col_blocks + w] = bits;                                       // :94
+}
+
 }  // namespace phnms

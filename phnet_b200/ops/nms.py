@@ -39,14 +39,14 @@ def _check_inputs(boxes: torch.Tensor, scores: torch.Tensor, batched: bool):
         raise RuntimeError("boxes and scores must be on the same device")
     if not boxes.is_contiguous():
         raise RuntimeError("boxes must be contiguous")
-    if boxes.dtype != torch.float32:
-        raise RuntimeError(f"nms_cuda_forward not implemented for '{boxes.dtype}' (this build computes in float32 only)")
+    if boxes.dtype not in (torch.float32, torch.float64):     # AT_DISPATCH_FLOATING_TYPES: float and double only
+        raise RuntimeError(f"\"nms_cuda_forward\" not implemented for '{boxes.dtype}'")
     want = 3 if batched else 2
     if boxes.dim() != want:
         raise RuntimeError(f"boxes must have {want} dimensions, got {boxes.dim()}")
     if boxes.shape[-1] < 6:
         raise RuntimeError("Wrong number of offsets. Rows are 5 + n_offsets wide")
-    if scores.dtype != torch.float32:
+    if scores.dtype != torch.float32 and boxes.dtype == torch.float32:
         scores = scores.float()          # the reference sorts whatever dtype it is given; order is unchanged
     if not scores.is_contiguous():
         scores = scores.contiguous()     # `scores.sort` accepts strided input (nms.cpp:51)
@@ -106,6 +106,29 @@ def _launch(boxes, scores, n_valid, F, N, n_off, overlap, top_k, sort_model, tun
     _capi.check(rc)
 
 
+def _launch_f64(boxes, scores, n_valid, F, N, n_off, overlap, top_k, keep, num, parent):
+    """Double boxes (the reference dispatches over float and double, nms_kernel.cu:171): the ordering is torch's own
+    `scores.sort(..., descending=True)` -- literally what the reference calls (nms.cpp:51), so ties fall the same way --
+    and the bitmask + scan kernels of the C ABI do the rest in fp64."""
+    top_k = int(top_k)
+    if top_k < 0:
+        raise TypeError("top_k must be non-negative (unsigned long in the reference, nms.cpp:48)")
+    if n_valid is not None:
+        raise RuntimeError("n_valid is not supported for float64 boxes")
+    L = _capi.lib()
+    dev = boxes.device
+    with torch.cuda.device(dev):
+        order = scores.sort(-1, True)[1].contiguous()
+        nbytes = int(L.phnms_ordered_f64_workspace_bytes(F, N))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = L.phnms_forward_ordered_f64(boxes.data_ptr(), order.data_ptr(), None, F, N, n_off, float(overlap), top_k,
+                                         keep.data_ptr(), num.data_ptr(), parent.data_ptr(), ws.data_ptr(), nbytes,
+                                         torch.cuda.current_stream(dev).cuda_stream)
+        ws.record_stream(torch.cuda.current_stream(dev))
+        order.record_stream(torch.cuda.current_stream(dev))
+    _capi.check(rc)
+
+
 def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model: int = _capi.SORT_TORCH_CUDA,
         tuning=None):
     """Drop-in for `libs.ops.nms` (libs/ops/nms.py:32).
@@ -117,7 +140,10 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model
     N, P = boxes.shape
     out = torch.empty(2 * N + 1, dtype=torch.int64, device=boxes.device)   # one allocation, three views
     keep, parent, num = out[:N], out[N:2 * N], out[2 * N]
-    _launch(boxes, scores, None, 1, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent)
+    if boxes.dtype == torch.float64:
+        _launch_f64(boxes, scores, None, 1, N, P - 5, overlap, top_k, keep, num, parent)
+    else:
+        _launch(boxes, scores, None, 1, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent)
     return [keep, num, parent]
 
 
@@ -144,7 +170,12 @@ def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, n_val
         parent = torch.empty((F, N), dtype=torch.int64, device=dev)
     else:
         keep, num, parent = out
-    _launch(boxes, scores, n_valid, F, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent, collect)
+    if boxes.dtype == torch.float64:
+        if collect is not None:
+            raise RuntimeError("collect is not supported for float64 boxes")
+        _launch_f64(boxes, scores, n_valid, F, N, P - 5, overlap, top_k, keep, num, parent)
+    else:
+        _launch(boxes, scores, n_valid, F, N, P - 5, overlap, top_k, sort_model, tuning, keep, num, parent, collect)
     return keep, num, parent
 
 

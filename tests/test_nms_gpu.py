@@ -225,7 +225,10 @@ def test_error_behaviour(cuda_device):
     with pytest.raises(RuntimeError):
         nms(p.t().contiguous().t(), s, 50, 4)        # CHECK_CONTIGUOUS (nms.cpp:41)
     with pytest.raises(RuntimeError):
-        nms(p.double(), s, 50, 4)                    # float32 only
+        nms(p.half(), s.half(), 50, 4)               # AT_DISPATCH_FLOATING_TYPES: float and double only (nms_kernel.cu:171)
+    kd, nd, pd = nms(p.double(), s.double(), 50, 4)  # double is dispatched (tests/test_f64.py has the parity cases)
+    kf, nf, pf = nms(p, s, 50, 4)
+    assert int(nd) == int(nf) and torch.equal(kd, kf) and torch.equal(pd, pf)
     with pytest.raises(RuntimeError):
         nms(p[:, :5].contiguous(), s, 50, 4)         # wrong number of offsets (nms_kernel.cu:154)
     with pytest.raises(RuntimeError):
