@@ -13,6 +13,13 @@
 //   * the per-round exchange between the CTAs of a cluster uses st.async (remote shared-memory stores that complete
 //     a transaction count on the RECEIVER's mbarrier) instead of barrier.cluster, whose release/acquire compiles to
 //     MEMBAR.ALL.GPU + ERRBAR + UCGABAR and was ~20 % of all stall samples.
+//   * the first batch of a frame is PLANNED by phnms_topm_kernel (candidates, their mutual predicate, the greedy scan
+//     over them, their keep[] entries): the kept candidates are known up front and evaluated two per pass over the
+//     registers (freg_eval_multi: independent fp32 chains, FADD2 subtractions) with no selection, exchange or barrier.
+//     Only frames whose candidates run out before top_k lanes are kept enter the fallback batches (cluster exchange).
+//   * what bounds it now: latency inside the CTA -- the phases of a frame run one after the other in
+//     all 16 warps, 4 warps per scheduler because 72 offsets live in registers (128 registers / thread, zero spills:
+//     every additional live value in the frame loop spills and costs 10-15 %).
 //
 // Reference semantics: libs/ops/csrc/nms.cpp:51 (ordering), nms_kernel.cu:26-48 (devIoU), :50-96 (mask), :99-143 (collect).
 #pragma once
@@ -34,8 +41,8 @@ constexpr int kHdr = 32;   // candidate header bytes: {key, index, start, end, m
 //   key/index : rank key (key << 32 | index orders the frame), original proposal index
 //   start/end : the lane's own bounds (nms_kernel.cu:29-34), end clamped to n_off-1
 //   mask0..2  : the lane's in-range bitmask over row words (range_mask)
-//   aux       : precomputed records: number of valid candidates of the frame (record 0);
-//               compacted fallback headers: index of the slot that holds the row
+//   aux       : candidate block: adjacency bits << 16 | number of valid candidates (slot 1: | the kept set of the planned
+//               greedy scan instead of the count); compacted fallback headers: index of the slot that holds the row
 struct FregLayout {
     int off_wtop;     // 2 parities x 32 warps x kCand x u64: per-warp best alive keys
     int off_bh;       // 32 x 32 B compacted headers of a fallback batch, in rank order; then count; then 3 x 32 dead flags
