@@ -95,8 +95,12 @@ __device__ __forceinline__ bool pair_hit_scalar(const float *a, const float *b, 
     if (end < start) return false;                                  // :36
     const int i0 = (int)(((uint32_t)start + 5u) & 255u);            // :38 unsigned char counter
     const int last = (int)((uint32_t)end + 5u);
+    const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
+    const float lim = __fmul_rn(thr, (float)len);                   // :46
     float dist = 0.0f;
     int i = i0;
+    // Exact early exit: every term is >= 0 and fp32 addition is monotone, so once the running sum has reached the limit the
+    // final `dist < lim` is false whatever follows (a NaN makes both comparisons false and the loop simply runs on).
     for (; i + 3 <= last; i += 4) {   // loads of four offsets in flight, the adds stay sequential and in order
         const float a0 = a[i], a1 = a[i + 1], a2 = a[i + 2], a3 = a[i + 3];
         const float b0 = b[i], b1 = b[i + 1], b2 = b[i + 2], b3 = b[i + 3];
@@ -104,10 +108,10 @@ __device__ __forceinline__ bool pair_hit_scalar(const float *a, const float *b, 
         dist = __fadd_rn(dist, fabsf(__fsub_rn(a1, b1)));
         dist = __fadd_rn(dist, fabsf(__fsub_rn(a2, b2)));
         dist = __fadd_rn(dist, fabsf(__fsub_rn(a3, b3)));
+        if (dist >= lim) return false;
     }
     for (; i <= last; ++i) dist = __fadd_rn(dist, fabsf(__fsub_rn(a[i], b[i])));
-    const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
-    return dist < __fmul_rn(thr, (float)len);                       // :46
+    return dist < lim;
 }
 
 // ---- warp helpers --------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ namespace phnms {
 
 constexpr int kCand = 4;   // candidates every CTA publishes per exchange (fallback batches)
 constexpr int kTopM = 16;  // capacity: per-frame best-ranked proposals precomputed by phnms_topm_kernel (first batch);
-                           // FusedParams::topm_count (8 for top_k <= 4, else 16) of them are produced and fetched
+                           // FusedParams::topm_count (8 or 12 for top_k <= 4, else 16) of them are produced and fetched
 constexpr int kPlanLanes = 2;    // kept lanes of the planned batch evaluated per pass, one proposal per thread (n_off 72 / small frames)
 constexpr int kPlanLanes2 = 2;   // same, two proposals per thread (n_off 36): chains per thread = lanes x 2
 constexpr bool kSkipGroups = true;   // warp-uniform skip of 8-word groups outside the kept lane's own range

@@ -484,7 +484,15 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
                 fp.claim_ctr = dynamic ? claim_ctr : nullptr;
             }
             // enough candidates that the first batch usually reaches top_k without an exchange
-            const int topm_count = (top_k > 0 && top_k <= 4) ? 8 : kTopM;
+            // Candidates per frame.  With top_k <= 4 eight of them leave ~14 % of the frames short of top_k kept lanes (those
+            // frames pay a fallback batch: cluster exchange, barriers), twelve ~3 %, sixteen ~0.5 % -- but every candidate
+            // costs time in the top-M kernel (one warp per frame) whatever the frame size.  Measured: N = 1000 x 72:
+            // 14.9 / 15.6 / 15.4 M frames/s with 8 / 12 / 16; N = 240: 53.9 / 51.4 / 48.1 M.
+            int topm_count = (top_k > 0 && top_k <= 4) ? (N > 384 ? 12 : 8) : kTopM;
+            if (const char *ev = getenv("PHNMS_TOPM_COUNT")) {   // experiment knob: candidates per frame (2 .. kTopM)
+                const int v = atoi(ev);
+                if (v >= 2 && v <= kTopM) topm_count = v;
+            }
             fp.topm_count = topm_count;
             {
                 int warps = kTopmWarps;
