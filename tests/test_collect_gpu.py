@@ -55,6 +55,6 @@ def test_two_gpu_peer_collection():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29631", os.path.join(ROOT, "scripts", "peer_check.py")]
+           "--master-port", "29631", os.path.join(ROOT, "tests", "peer_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "peer collection ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
