@@ -387,14 +387,13 @@ int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int6
 
 static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                         float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
-                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len,
-                        const phnms_collect *collect);
+                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len);
 
 int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                       float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
                       void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_) {
     return forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
-                        tuning, stream_, nullptr, 0, nullptr);
+                        tuning, stream_, nullptr, 0);
 }
 
 int phnms_forward_f32_trace(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
@@ -402,7 +401,7 @@ int phnms_forward_f32_trace(const float *props, const float *scores, const int32
                             int64_t *parent, void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_,
                             int64_t *trace, int trace_len) {
     return forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
-                        tuning, stream_, trace, trace_len, nullptr);
+                        tuning, stream_, trace, trace_len);
 }
 
 int phnms_forward_collect_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,
@@ -415,7 +414,7 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
     for (int d = 0; d < collect->n_dst; ++d)
         if (!collect->dst[d] || ((uintptr_t)collect->dst[d] & 7u)) return PHNMS_ERR_BAD_ARG;
     int rc = forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws,
-                          ws_bytes, tuning, stream_, nullptr, 0, collect);
+                          ws_bytes, tuning, stream_, nullptr, 0);
     if (rc != PHNMS_OK || F == 0) return rc;
     CollectArgs ca;
     ca.n = collect->n_dst;
@@ -429,8 +428,7 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
 
 static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                         float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
-                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len,
-                        const phnms_collect *collect) {
+                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len) {
     int rc = check_shape(F, N, n_off);
     if (rc != PHNMS_OK) return rc;
     if (sort_model < 0 || sort_model > 2 || top_k < 0) return PHNMS_ERR_BAD_ARG;
