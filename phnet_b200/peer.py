@@ -52,21 +52,41 @@ class PeerCollector:
         self.flag_off = self.nbuf * self.buf_bytes
         self.nbytes = self.flag_off + 256                     # flags: one uint64 per rank, then an int status word
         L = _capi.lib()
+        # Every rank walks through the same collectives whatever happens locally: a rank that cannot allocate or map
+        # publishes the failure instead of leaving the others waiting in a collective, and then ALL ranks raise.
+        self.local, self.base, err = 0, [], None
         with torch.cuda.device(self.dev):
-            ptr = ctypes.c_void_p()
             handle = ctypes.create_string_buffer(_capi.IPC_HANDLE_BYTES)
-            _capi.check(L.phnms_peer_alloc(self.nbytes, ctypes.byref(ptr), handle))
-            self.local = int(ptr.value)
+            try:
+                ptr = ctypes.c_void_p()
+                _capi.check(L.phnms_peer_alloc(self.nbytes, ctypes.byref(ptr), handle))
+                self.local = int(ptr.value)
+            except Exception as e:   # noqa: BLE001
+                err = f"rank {self.rank}: peer_alloc: {e}"
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.base = []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.base.append(self.local)
-                    continue
-                q = ctypes.c_void_p()
-                _capi.check(L.phnms_peer_open(handles[r], ctypes.byref(q)))
-                self.base.append(int(q.value))
+            dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
+            if err is None and any(h is None for h in handles):
+                err = "a peer could not allocate its buffer"
+            if err is None:
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            self.base.append(self.local)
+                            continue
+                        q = ctypes.c_void_p()
+                        _capi.check(L.phnms_peer_open(handles[r], ctypes.byref(q)))
+                        self.base.append(int(q.value))
+                except Exception as e:   # noqa: BLE001
+                    err = f"rank {self.rank}: peer_open: {e}"
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)
+            if any(e is not None for e in errs):
+                for r, b in enumerate(self.base):
+                    if r != self.rank:
+                        L.phnms_peer_close(b)
+                if self.local:
+                    L.phnms_peer_free(self.local)
+                raise RuntimeError("peer memory unavailable: " + "; ".join(e for e in errs if e is not None))
         self._signal_dst = (ctypes.c_void_p * self.world)(*[b + self.flag_off + 8 * self.rank for b in self.base])
         self._mem = torch.as_tensor(_RawDeviceMemory(self.local, self.nbytes), device=self.dev)
         self.closed = False
