@@ -113,3 +113,28 @@ def test_install_as_libs_ops():
     assert shim is nms
     for k in ("libs", "libs.ops", "libs.ops.nms"):
         sys.modules.pop(k, None)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/phnms.h is the drop-in boundary for any host language: it must compile as C (and as C++) on its own, and a C
+    program linked against libphnms.so must resolve the entry points."""
+    import subprocess
+    src = tmp_path / "use_phnms.c"
+    src.write_text('#include "phnms.h"\n'
+                   '#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    phnms_plan pl; phnms_collect c; c.n_dst = 0; (void)c;\n'
+                   '    int rc = phnms_plan_query(16, 1000, 72, 0, &pl);\n'
+                   '    printf("%d %d %d %d %zu\\n", phnms_abi_version(), rc, pl.cluster, pl.threads, phnms_workspace_bytes(1, 40000, 72, 0));\n'
+                   '    return phnms_forward_f32(0, 0, 0, 1, 10, 0, 50.f, 4, 0, 0, 0, 0, 0, 0, 0, 0) == PHNMS_ERR_N_OFFSETS ? 0 : 1;\n'
+                   '}\n')
+    inc = os.path.join(ROOT, "include")
+    so_dir = os.path.dirname(_capi.SO_PATH)
+    exe = tmp_path / "use_phnms"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe), "-L", so_dir,
+                    "-l:libphnms.so", f"-Wl,-rpath,{so_dir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ver, rc, cluster, threads, ws = out.stdout.split()
+    assert int(ver) == _capi.ABI_VERSION and int(rc) == 0 and int(cluster) == 2 and int(threads) == 512 and int(ws) > 0
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-x", "c++", os.path.join(inc, "phnms.h")], check=True)
