@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PHNMS_ABI_VERSION 4
+#define PHNMS_ABI_VERSION 5
 
 #define PHNMS_OK 0
 #define PHNMS_ERR_BAD_ARG (-1)      /* null pointer, negative size, misaligned pointer                         */
@@ -50,8 +50,13 @@ extern "C" {
 #define PHNMS_PATH_TILED 2          /* three kernels: radix order -> 64x64 tile bitmask -> warp-ballot greedy scan     */
 
 /* variants of the fused path */
-#define PHNMS_FUSED_SMEM 1          /* proposals stay in shared memory; any n_off in [1, 250]                          */
-#define PHNMS_FUSED_REG 2           /* proposals held in registers, next frame's TMA load overlaps compute; n_off 36/72 */
+#define PHNMS_FUSED_SMEM 1          /* cluster per frame, proposals stay in shared memory; any n_off in [1, 250]       */
+#define PHNMS_FUSED_REG 2           /* cluster per frame, proposals held in registers, next frame's TMA load overlaps
+                                       compute; n_off 36/72, any top_k                                                 */
+#define PHNMS_FUSED_STREAM 3        /* the default for n_off 36/72 and 1 <= top_k <= 8: a select kernel runs the greedy scan
+                                       on the few best-ranked proposals it needs, a streaming kernel (independent warps,
+                                       TMA-fed, no cluster) evaluates every proposal against the kept lanes; frames the
+                                       select kernel could not finish are redone by the PHNMS_FUSED_REG kernel          */
 
 /* how frames are handed to the persistent clusters of the register-resident kernel */
 #define PHNMS_SCHED_STATIC 1        /* cluster c takes frames c, c + n_clusters, ...: fastest when the GPU is not shared         */
@@ -62,9 +67,14 @@ typedef struct phnms_tuning {
     int cluster;         /* CTAs per frame for the fused path: 1,2,4,8,16            (0 = auto) */
     int threads;         /* threads per CTA for the fused path: multiple of 32, <=512 (0 = auto) */
     int max_clusters;    /* cap on resident clusters (persistent grid size)          (0 = auto) */
-    int variant;         /* fused path: PHNMS_FUSED_SMEM or PHNMS_FUSED_REG          (0 = auto) */
+    int variant;         /* fused path: PHNMS_FUSED_SMEM / _REG / _STREAM            (0 = auto) */
     int schedule;        /* register-resident kernel: PHNMS_SCHED_STATIC / _DYNAMIC   (0 = auto) */
+    int stream_warps;    /* streaming kernel: warps per CTA, 1..16                   (0 = auto) */
+    int select_cap;      /* select kernel: proposals drawn per frame before the frame is handed to the resume
+                            pass, >= 8                                               (0 = auto: 64) */
+    int lanes_per_pass;  /* streaming kernel: kept lanes evaluated per pass over the registers, 1/2/4 (0 = auto) */
 } phnms_tuning;
+/* cluster, threads and schedule describe the cluster kernels; setting any of them (or variant 1/2) selects those kernels. */
 
 typedef struct phnms_plan {
     int path;            /* PHNMS_PATH_FUSED or PHNMS_PATH_TILED */
@@ -74,7 +84,7 @@ typedef struct phnms_plan {
     int smem_bytes;      /* dynamic shared memory per CTA */
     int grid;            /* CTAs launched */
     int launches;        /* kernel launches one phnms_forward_f32 call makes */
-    int variant;         /* PHNMS_FUSED_SMEM / PHNMS_FUSED_REG (fused path), 0 otherwise */
+    int variant;         /* PHNMS_FUSED_SMEM / _REG / _STREAM (fused path), 0 otherwise */
     int cols_per_thread; /* proposals held per thread (register-resident variant) */
     int max_active_clusters; /* cudaOccupancyMaxActiveClusters for this launch (0 when no device was queried) */
     size_t workspace_bytes;
@@ -83,11 +93,16 @@ typedef struct phnms_plan {
 int phnms_abi_version(void);
 const char *phnms_error_string(int code);
 
-/* Bytes of device workspace `phnms_forward_f32` needs for this shape (0 for the fused path). */
+/* Bytes of device workspace `phnms_forward_f32` needs for this shape, whatever top_k is passed: the per-frame kept-lane
+ * blocks of the streaming path / candidate blocks of the register-resident cluster kernel (a few KB per frame), the order
+ * and bitmask of the tiled path; 0 only for the shared-memory cluster kernel (n_off other than 36 / 72). */
 size_t phnms_workspace_bytes(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning /* nullable */);
 
-/* Fills `plan` with what phnms_forward_f32 would launch for this shape on the current device. */
+/* Fills `plan` with what phnms_forward_f32 would launch for this shape on the current device (top_k: as in the call;
+ * phnms_plan_query assumes a top_k in [1, 8], PHNet's 4 / 8). */
 int phnms_plan_query(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning /* nullable */, phnms_plan *plan);
+int phnms_plan_query_topk(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning *tuning /* nullable */,
+                          phnms_plan *plan);
 
 /*
  * Lane NMS over a batch of F independent frames (F = 1 is exactly one reference `nms` call).
@@ -161,14 +176,16 @@ int phnms_decode_lanes_f32(const float *rows, const int64_t *num, int64_t T, int
  * address the current device can store to: local memory, or another GPU's buffer mapped into this process
  * (phnms_peer_open) -- then the records travel over NVLink / NVSwitch.  With every rank passing the buffers of all ranks
  * and row0 = rank * F, each rank ends up holding the records of all frames: an all-gather without a collective call
- * (one extra ~2 us launch in the same call).  Requires top_k >= 1.  Completion across GPUs: phnms_peer_sync.
+ * (one extra ~2 us launch in the same call).  Requires top_k >= 1; PHNMS_ERR_BAD_ARG unless width == top_k + 1 and
+ * row0 + F <= rows (a record is never stored outside a destination).  Completion across GPUs: phnms_peer_sync.
  */
 #define PHNMS_MAX_DST 16
 typedef struct phnms_collect {
     int n_dst;                        /* destinations, 1 .. PHNMS_MAX_DST                              */
-    int reserved;
+    int width;                        /* row width of every destination: must equal top_k + 1          */
     int64_t row0;                     /* row of this call's frame 0 in every destination               */
-    int64_t *dst[PHNMS_MAX_DST];      /* device-accessible [rows, top_k + 1] int64 buffers, 8-byte aligned */
+    int64_t rows;                     /* rows of every destination: row0 + F must not exceed it        */
+    int64_t *dst[PHNMS_MAX_DST];      /* device-accessible [rows, width] int64 buffers, 8-byte aligned   */
 } phnms_collect;
 
 int phnms_forward_collect_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,

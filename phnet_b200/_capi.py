@@ -8,24 +8,28 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("PHNMS_SO") or os.path.join(HERE, "csrc", "libphnms.so")   # PHNMS_SO: A/B testing of builds
 
 PATH_AUTO, PATH_FUSED, PATH_TILED = 0, 1, 2
-FUSED_SMEM, FUSED_REG = 1, 2
+FUSED_SMEM, FUSED_REG, FUSED_STREAM = 1, 2, 3
 SCHED_STATIC, SCHED_DYNAMIC = 1, 2
 SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
 
 EXPORTS = (
-    "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query",
+    "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query", "phnms_plan_query_topk",
     "phnms_forward_f32", "phnms_forward_f32_trace", "phnms_order_workspace_bytes", "phnms_order_f32",
     "phnms_get_lanes_workspace_bytes", "phnms_get_lanes_f32",
     "phnms_decode_lanes_f32", "phnms_line_iou_f32", "phnms_ordered_f64_workspace_bytes", "phnms_forward_ordered_f64", "phnms_forward_collect_f32", "phnms_peer_alloc", "phnms_peer_open", "phnms_peer_close", "phnms_peer_free", "phnms_peer_sync",
 )
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_DST = 16
 IPC_HANDLE_BYTES = 64
 
 
 class Tuning(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int), ("cluster", ctypes.c_int), ("threads", ctypes.c_int),
-                ("max_clusters", ctypes.c_int), ("variant", ctypes.c_int), ("schedule", ctypes.c_int)]
+                ("max_clusters", ctypes.c_int), ("variant", ctypes.c_int), ("schedule", ctypes.c_int),
+                ("stream_warps", ctypes.c_int), ("select_cap", ctypes.c_int), ("lanes_per_pass", ctypes.c_int)]
+
+    def key(self):
+        return tuple(getattr(self, k) for k, _ in self._fields_)
 
 
 class Plan(ctypes.Structure):
@@ -40,15 +44,16 @@ class Plan(ctypes.Structure):
 
 class Collect(ctypes.Structure):
     """phnms_collect: where the compact kept-lane records of a call go (include/phnms.h)."""
-    _fields_ = [("n_dst", ctypes.c_int), ("reserved", ctypes.c_int), ("row0", ctypes.c_int64),
+    _fields_ = [("n_dst", ctypes.c_int), ("width", ctypes.c_int), ("row0", ctypes.c_int64), ("rows", ctypes.c_int64),
                 ("dst", ctypes.c_void_p * MAX_DST)]
 
 
-def collect(dst_ptrs, row0: int = 0) -> Collect:
+def collect(dst_ptrs, rows: int, width: int, row0: int = 0) -> Collect:
+    """Destinations are [rows, width] int64 buffers; the call that uses this stores its frames at rows row0 .. row0 + F."""
     if not 1 <= len(dst_ptrs) <= MAX_DST:
         raise ValueError(f"between 1 and {MAX_DST} collection buffers")
     c = Collect()
-    c.n_dst, c.reserved, c.row0 = len(dst_ptrs), 0, int(row0)
+    c.n_dst, c.width, c.row0, c.rows = len(dst_ptrs), int(width), int(row0), int(rows)
     for i, ptr in enumerate(dst_ptrs):
         c.dst[i] = int(ptr)
     return c
@@ -82,6 +87,8 @@ def lib() -> ctypes.CDLL:
     L.phnms_workspace_bytes.restype = sz
     L.phnms_plan_query.argtypes = [i64, i64, ci, ctypes.POINTER(Tuning), ctypes.POINTER(Plan)]
     L.phnms_plan_query.restype = ci
+    L.phnms_plan_query_topk.argtypes = [i64, i64, ci, i64, ctypes.POINTER(Tuning), ctypes.POINTER(Plan)]
+    L.phnms_plan_query_topk.restype = ci
     L.phnms_forward_f32.argtypes = [vp, vp, vp, i64, i64, ci, ctypes.c_float, i64, ci, vp, vp, vp, vp, sz,
                                     ctypes.POINTER(Tuning), vp]
     L.phnms_forward_f32.restype = ci
@@ -131,13 +138,14 @@ def check(code: int) -> None:
         raise PhnmsError(code, lib().phnms_error_string(code).decode())
 
 
-def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0, variant: int = 0, schedule: int = 0):
-    if not (path or cluster or threads or max_clusters or variant or schedule):
+def tuning(path: int = 0, cluster: int = 0, threads: int = 0, max_clusters: int = 0, variant: int = 0, schedule: int = 0,
+           stream_warps: int = 0, select_cap: int = 0, lanes_per_pass: int = 0):
+    if not (path or cluster or threads or max_clusters or variant or schedule or stream_warps or select_cap or lanes_per_pass):
         return None
-    return Tuning(path, cluster, threads, max_clusters, variant, schedule)
+    return Tuning(path, cluster, threads, max_clusters, variant, schedule, stream_warps, select_cap, lanes_per_pass)
 
 
-def plan(F: int, N: int, n_off: int, tune: Tuning | None = None) -> dict:
+def plan(F: int, N: int, n_off: int, tune: Tuning | None = None, top_k: int = -1) -> dict:
     p = Plan()
-    check(lib().phnms_plan_query(F, N, n_off, ctypes.byref(tune) if tune else None, ctypes.byref(p)))
+    check(lib().phnms_plan_query_topk(F, N, n_off, int(top_k), ctypes.byref(tune) if tune else None, ctypes.byref(p)))
     return p.as_dict()

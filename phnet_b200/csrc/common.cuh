@@ -157,18 +157,36 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded: a wait that has not completed after kMbarTimeoutNs traps (the launch fails with an error the caller sees)
+// instead of hanging the GPU -- a protocol bug must never become a hung box.  The clock is only read on the slow path.
+constexpr unsigned long long kMbarTimeoutNs = 4000000000ull;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
         : "memory");
+    return ok != 0u;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        for (int i = 0; i < 64; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > kMbarTimeoutNs) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int i = 0; i < 16; ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity);
 }
 // Debug variant: gives up after ~2^22 polls and appends {tag, block, thread, parity, a, b} to `dbg` (first word = count).
 __device__ __forceinline__ bool mbar_wait_watch(uint32_t bar, uint32_t parity, long long *dbg, int tag, long long a,

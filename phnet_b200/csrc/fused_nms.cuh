@@ -53,6 +53,8 @@ struct FusedParams {
     const int *topm;   // optional [F, kTopM] candidate slots (header + row) of the best-ranked proposals (phnms_topm_kernel)
     int topm_count;    // candidate slots per frame in `topm` (<= kTopM)
     unsigned long long *claim_ctr;   // frame-claim counter (zero before the launch); register-resident kernel only
+    const int *frame_list;           // optional: the kernel works through frame_list[0 .. *frame_count) instead of 0 .. F
+    const unsigned int *frame_count; //           (the resume list of the streaming path, stream.cuh); static schedule only
     long long *trace;  // optional: CTA 0 / thread 0 writes clock64() at phase boundaries (phnms_forward_f32_trace)
     int trace_len;
 };

@@ -575,7 +575,10 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
             __syncthreads();
         }
     }
-    long long f = dyn ? claim_slot[0] : cl, f_next = dyn ? f + 1 : cl + ncl;
+    // Resume mode (static schedule only): the frames come from a device-side list -- `fi` walks the list, `f` is the frame.
+    const long long Fn = p.frame_list ? (long long)*p.frame_count : p.F;
+    auto frame_at = [&](long long i) -> long long { return (p.frame_list && i < Fn) ? (long long)p.frame_list[i] : i; };
+    long long fi = dyn ? claim_slot[0] : cl, fi_next = dyn ? fi + 1 : cl + ncl;
     __syncthreads();   // everyone has read slot 0 before a claim may overwrite it
     if (tid == 0) {
         mbar_init(bar_claim0, 1);
@@ -603,14 +606,17 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
         *reinterpret_cast<int4 *>(smem + 80) = make_int4((int)s0.total, (int)s0.chunk, s0.tail0, s0.ntail);
     }
     __syncthreads();
-    if (f < p.F)
-        request_slab(p, f, slab_geometry(p, f, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P, pslots,
+    if (fi < Fn) {
+        const long long f0 = frame_at(fi);
+        request_slab(p, f0, slab_geometry(p, f0, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P, pslots,
                      (uint32_t)(p.topm_count * SLOT), sbuf, sbulk);
+    }
     // Threads beyond this CTA's rows ("spare lanes") hold register copies of the batch's candidates, so that every CTA
     // can tell -- without talking to its peers -- which candidates an earlier winner of the same batch suppressed.
     const int lcap = min(T * CPT - p.rpc, 31);
 
-    for (; f < p.F; f = f_next, ++iter) {
+    for (; fi < Fn; fi = fi_next, ++iter) {
+        const long long f = frame_at(fi);
         PHNMS_TRACE(1);  // frame start
         const uint32_t fpar = iter & 1u;   // parity of the double-buffered candidate block / scores
         if (dyn && csize > 1) cluster_arrive_relaxed();
@@ -683,18 +689,20 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
 
         // ---- request the next frame now; it lands while this frame's rounds run ----------------------------------
         if (!dyn) {
-            f_next = f + ncl;
+            fi_next = fi + ncl;
         } else if (iter > 0) {   // the frame after this one: claimed during the previous iteration, sent in its middle
             const uint32_t cp_ = (iter - 1u) & 1u;
             if (csize > 1) mbar_wait(bar_claim0 + 8u * cp_, ((iter - 1u) >> 1) & 1u);
-            f_next = claim_slot[cp_];
+            fi_next = claim_slot[cp_];
         }
-        const bool more = f_next < p.F;   // (uniform over the cluster) another iteration follows
+        const bool more = fi_next < Fn;   // (uniform over the cluster) another iteration follows
         if (dyn && more && csize > 1 && tid == 0) mbar_arrive_expect_tx(bar_claim0 + 8u * (iter & 1u), 8u);
-        if (more)
+        if (more) {
+            const long long f_next = frame_at(fi_next);
             request_slab(p, f_next, slab_geometry(p, f_next, rank, P, T, geo_uniform, geo), rows_buf, bar_load, tid, T, P,
                          pslots + (size_t)(fpar ^ 1u) * kTopM * L.slot_stride, (uint32_t)(p.topm_count * SLOT),
                          sbuf + (fpar ^ 1u) * sbuf_stride, sbulk);
+        }
         PHNMS_TRACE(4);  // next slab requested
         // hand the claimed frame index to the cluster; peers read it after the second barrier of their next frame
         // (sent here, mid-frame, so that it is long there when they need it)

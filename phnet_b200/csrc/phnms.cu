@@ -9,10 +9,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "fused_nms.cuh"
 #include "fused_reg.cuh"
 #include "tiled_nms.cuh"
 #include "topm.cuh"
+#include "select.cuh"
+#include "stream.cuh"
 #include "frontend.cuh"
 
 using namespace phnms;
@@ -25,14 +29,75 @@ struct DeviceInfo {
     int cc_major;
 };
 
+// Device attributes are cached per device: a per-frame call (the way PHNet calls the op) must not pay three attribute
+// queries each time.  Benign race: concurrent first calls write identical values.
 int device_info(DeviceInfo *d) {
+    static DeviceInfo cache[64];
+    static volatile int ready[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64 && ready[dev]) {
+        *d = cache[dev];
+        return 0;
+    }
     cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     e = cudaDeviceGetAttribute(&d->cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) {
+        cache[dev] = *d;
+        __sync_synchronize();
+        ready[dev] = 1;
+    }
     return (int)e;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): raised to the device's opt-in maximum.
+// (keyed by the function's address: several template instances share one pointer TYPE)
+int ensure_max_smem(const void *kern, int smem_optin) {
+    struct Entry { const void *fn; int dev; };
+    static Entry table[256];
+    static int count = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (int i = 0; i < count; ++i)
+            if (table[i].fn == kern && table[i].dev == dev) return 0;
+    }
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return (int)e;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    std::lock_guard<std::mutex> g(mu);
+    if (count < 256) table[count++] = Entry{kern, dev};
+    return 0;
+}
+
+// experiment knobs of debug sessions, read once at load (never on the call path)
+struct EnvKnobs {
+    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, no_stream, debug, skip;
+    EnvKnobs() {
+        auto geti = [](const char *n) { const char *v = getenv(n); return v ? atoi(v) : 0; };
+        topm_count = geti("PHNMS_TOPM_COUNT");
+        no_topm = getenv("PHNMS_NO_TOPM") != nullptr;
+        select_cap = geti("PHNMS_SELECT_CAP");
+        lanes_per_pass = geti("PHNMS_LANES_PER_PASS");
+        stream_warps = geti("PHNMS_STREAM_WARPS");
+        no_stream = getenv("PHNMS_NO_STREAM") != nullptr;
+        debug = getenv("PHNMS_DEBUG") != nullptr;
+        skip = geti("PHNMS_SKIP");   // timing experiments only (results are wrong): 1 = no select, 2 = no stream, 4 = no resume
+    }
+};
+const EnvKnobs g_env;
+
+// PHNMS_DEBUG=1: say on stderr which step of a call failed (the return code alone does not)
+int fail_at(const char *step, int code) {
+    if (code != 0 && g_env.debug) fprintf(stderr, "phnms: %s failed: %d (%s)\n", step, code, code > 0 ? cudaGetErrorString((cudaError_t)code) : "argument");
+    return code;
 }
 
 int check_shape(int64_t F, int64_t N, int n_off) {
@@ -48,12 +113,54 @@ size_t tiled_workspace(int64_t F, int64_t N) {
     return (size_t)F * N * 8 + (size_t)F * N * 16 + (size_t)F * N * cb * 8 + 256;
 }
 
+// Launch shape of the streaming kernel (stream.cuh): warps per CTA, how frames are cut into units when there are fewer
+// frames than SMs, the kept-block ring, the grid (one persistent CTA per SM).
+struct StreamShape {
+    int warps, ipf, nseg, ips, ks, block_bytes, grid;
+    StreamLayout L;
+    bool ok, bad_tuning;
+};
+
+StreamShape stream_shape(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning &t, int sms, int smem_max) {
+    StreamShape ss = {};
+    const int P = 5 + n_off;
+    ss.warps = t.stream_warps ? t.stream_warps : (g_env.stream_warps ? g_env.stream_warps : kStreamMaxWarps);
+    if (ss.warps < 1 || ss.warps > kStreamMaxWarps) {
+        ss.bad_tuning = true;
+        return ss;
+    }
+    ss.ipf = (int)((N + 31) / 32);
+    if (ss.ipf < 1) ss.ipf = 1;   // (N == 0 is answered before any launch; keep the arithmetic below defined)
+    ss.nseg = 1;
+    if (F < sms) ss.nseg = (int)((sms + F - 1) / (F > 0 ? F : 1));
+    if (ss.nseg > ss.ipf) ss.nseg = ss.ipf;
+    if (ss.nseg < 1) ss.nseg = 1;
+    ss.ips = (ss.ipf + ss.nseg - 1) / ss.nseg;
+    ss.nseg = (ss.ipf + ss.ips - 1) / ss.ips;
+    ss.ks = (ss.warps + ss.ips - 1) / ss.ips + 3;
+    if (ss.ks < 4) ss.ks = 4;
+    if (ss.ks > kStreamMaxRing) ss.ks = kStreamMaxRing;
+    const int kk = top_k < 0 ? kStreamMaxK : (int)top_k;
+    ss.block_bytes = kBlkHdr + kk * (kHdr + 4 * ((P + 3) & ~3));
+    ss.L = stream_layout(ss.warps, P, ss.block_bytes, ss.ks);
+    while (ss.L.total > smem_max && ss.ks > 4) ss.L = stream_layout(ss.warps, P, ss.block_bytes, --ss.ks);
+    while (ss.L.total > smem_max && ss.warps > 1) ss.L = stream_layout(--ss.warps, P, ss.block_bytes, ss.ks);
+    const long long units = (long long)F * ss.nseg;
+    long long grid = units < sms ? units : sms;
+    if (t.max_clusters > 0 && grid > t.max_clusters) grid = t.max_clusters;
+    if (grid < 1) grid = 1;
+    ss.grid = (int)grid;
+    ss.ok = ss.L.total <= smem_max && ((units + grid - 1) / grid + 1) * ss.ips < 0x7fffffffLL;
+    return ss;
+}
+
 // Decide what to launch.  No device queries when `dev` is null (shape-only planning with B200 constants).
-int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const DeviceInfo *dev, phnms_plan *pl) {
+// top_k < 0: unknown (shape-only queries) -- assume PHNet's range [1, 8].
+int make_plan(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning *tun, const DeviceInfo *dev, phnms_plan *pl) {
     const int P = 5 + n_off;
     const int smem_max = dev ? dev->smem_optin : 232448;
     const int sms = dev ? dev->sms : 148;
-    phnms_tuning t = {0, 0, 0, 0, 0, 0};
+    phnms_tuning t = phnms_tuning{};
     if (tun) t = *tun;
     pl->workspace_bytes = 0;
     pl->launches = 1;
@@ -70,6 +177,12 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
     if (t.path != PHNMS_PATH_TILED) {
         // ---- register-resident variant: n_off 36 / 72 only; a CTA holds at most 512 threads x cols_per_thread rows
         const bool reg_ok = (n_off == 36 || n_off == 72) && t.variant != PHNMS_FUSED_SMEM;
+        // The streaming path: the default when nothing asks for the cluster kernels.  Its resume pass IS the register-resident
+        // cluster kernel, so it needs that plan to exist (N <= 8192).
+        const bool k_ok = top_k < 0 || (top_k >= 1 && top_k <= kStreamMaxK);
+        const bool want_stream = t.variant == PHNMS_FUSED_STREAM ||
+                                 (t.variant == 0 && !t.cluster && !t.threads && !t.schedule && !g_env.no_stream);
+        if (t.variant == PHNMS_FUSED_STREAM && (!reg_ok || !k_ok || t.cluster || t.threads || t.schedule)) return PHNMS_ERR_TUNING;
         if (reg_ok) {
             const int max_cpt = (n_off == 36) ? 2 : 1;
             // The smallest cluster whose CTAs can hold their share of the frame.  Threads: one (n_off 72) or two (n_off 36)
@@ -125,10 +238,29 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
                 pl->smem_bytes = L.total;
                 pl->grid = (int)(clusters * csize);
                 pl->launches = 2;  // phnms_topm_kernel + phnms_freg_kernel
-                pl->workspace_bytes = (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 512;   // claim counter + candidate block per frame (capacity)
+                // claim counter + per frame: candidate block (capacity) of the cluster kernel, which also covers the kept-lane
+                // block of the streaming path (kStreamMaxK slots), + resume flag and list entry
+                pl->workspace_bytes = 1024 + (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 2 * (((size_t)F * 4 + 255) & ~(size_t)255);
+                if (want_stream && k_ok && F < 0x7fffffff) {
+                    const StreamShape ss = stream_shape(F, N, n_off, top_k, t, sms, smem_max);
+                    if (ss.bad_tuning) return PHNMS_ERR_TUNING;
+                    if (ss.ok) {
+                        pl->variant = PHNMS_FUSED_STREAM;
+                        pl->cluster = 1;
+                        pl->threads = ss.warps * 32;
+                        pl->cols_per_thread = 1;
+                        pl->rows_per_cta = ss.warps * 32;
+                        pl->smem_bytes = ss.L.total;
+                        pl->grid = ss.grid;
+                        pl->launches = 3;   // phnms_select_kernel + phnms_stream_kernel + the resume pass (phnms_freg_kernel)
+                        pl->max_active_clusters = ss.grid;
+                    } else if (t.variant == PHNMS_FUSED_STREAM) {
+                        return PHNMS_ERR_TUNING;
+                    }
+                }
                 return PHNMS_OK;
             }
-            if (t.variant == PHNMS_FUSED_REG) return PHNMS_ERR_TUNING;
+            if (t.variant == PHNMS_FUSED_REG || t.variant == PHNMS_FUSED_STREAM) return PHNMS_ERR_TUNING;
         } else if (t.variant == PHNMS_FUSED_REG) {
             return PHNMS_ERR_TUNING;
         }
@@ -191,12 +323,11 @@ int make_plan(int64_t F, int64_t N, int n_off, const phnms_tuning *tun, const De
 
 template <typename Kern>
 int configure_cluster(Kern kern, const phnms_plan &pl, cudaStream_t stream, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    if (pl.cluster > 8) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return (int)e;
-    }
+    DeviceInfo d;
+    int rc = device_info(&d);
+    if (rc) return rc;
+    rc = ensure_max_smem(reinterpret_cast<const void *>(kern), d.smem_optin);
+    if (rc) return rc;
     *cfg = cudaLaunchConfig_t{};
     cfg->gridDim = dim3((unsigned)pl.grid);
     cfg->blockDim = dim3((unsigned)pl.threads);
@@ -251,7 +382,7 @@ int fused_occupancy(const phnms_plan &pl, int n_off) {
 }
 
 void fit_grid_to_occupancy(phnms_plan *pl, int64_t F, int n_off, const phnms_tuning *tun) {
-    if (pl->path != PHNMS_PATH_FUSED) return;
+    if (pl->path != PHNMS_PATH_FUSED || pl->variant == PHNMS_FUSED_STREAM) return;
     const int occ = fused_occupancy(*pl, n_off);
     pl->max_active_clusters = occ;
     if (occ <= 0) return;
@@ -352,19 +483,23 @@ const char *phnms_error_string(int code) {
 size_t phnms_workspace_bytes(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning) {
     phnms_plan pl;
     if (check_shape(F, N, n_off) != PHNMS_OK) return 0;
-    if (make_plan(F, N, n_off, tuning, nullptr, &pl) != PHNMS_OK) return 0;
+    if (make_plan(F, N, n_off, -1, tuning, nullptr, &pl) != PHNMS_OK) return 0;
     return pl.workspace_bytes;
 }
 
-int phnms_plan_query(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning, phnms_plan *plan) {
+int phnms_plan_query_topk(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning *tuning, phnms_plan *plan) {
     if (!plan) return PHNMS_ERR_BAD_ARG;
     int rc = check_shape(F, N, n_off);
     if (rc != PHNMS_OK) return rc;
     DeviceInfo dev;
     const bool have_dev = device_info(&dev) == 0;
-    rc = make_plan(F, N, n_off, tuning, have_dev ? &dev : nullptr, plan);
+    rc = make_plan(F, N, n_off, top_k, tuning, have_dev ? &dev : nullptr, plan);
     if (rc == PHNMS_OK && have_dev && dev.cc_major == 10) fit_grid_to_occupancy(plan, F, n_off, tuning);
     return rc;
+}
+
+int phnms_plan_query(int64_t F, int64_t N, int n_off, const phnms_tuning *tuning, phnms_plan *plan) {
+    return phnms_plan_query_topk(F, N, n_off, -1, tuning, plan);
 }
 
 size_t phnms_order_workspace_bytes(int64_t F, int64_t N) {
@@ -411,6 +546,8 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
     if (!collect) return PHNMS_ERR_BAD_ARG;
     if (collect->n_dst < 1 || collect->n_dst > PHNMS_MAX_DST || collect->row0 < 0 || top_k < 1 || top_k > 0x7ffffff)
         return PHNMS_ERR_BAD_ARG;
+    // a record is never stored outside a destination: the buffers are [rows, width] and this call fills rows row0 .. row0+F
+    if ((int64_t)collect->width != top_k + 1 || F < 0 || collect->row0 + F > collect->rows) return PHNMS_ERR_BAD_ARG;
     for (int d = 0; d < collect->n_dst; ++d)
         if (!collect->dst[d] || ((uintptr_t)collect->dst[d] & 7u)) return PHNMS_ERR_BAD_ARG;
     int rc = forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws,
@@ -424,6 +561,106 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
     phnms_collect_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
         reinterpret_cast<const long long *>(keep), reinterpret_cast<const long long *>(num_keep), F, (int)N, (int)top_k, ca);
     return (int)cudaGetLastError();
+}
+
+// ---- the streaming path: select -> stream -> resume ----------------------------------------------------------------------
+static int launch_stream(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
+                         float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
+                         void *ws, size_t ws_bytes, const phnms_tuning *tuning, const DeviceInfo &dev, const phnms_plan &pl,
+                         cudaStream_t stream) {
+    if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
+    const phnms_tuning t = tuning ? *tuning : phnms_tuning{};
+    const int P = 5 + n_off, SLOT = kHdr + 4 * ((P + 3) & ~3);
+    const StreamShape ss = stream_shape(F, N, n_off, top_k, t, dev.sms, dev.smem_optin);
+    if (!ss.ok) return fail_at("stream shape", PHNMS_ERR_TUNING);
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    unsigned int *ctrs = reinterpret_cast<unsigned int *>(base + 64);          // (the cluster kernel's claim counter sits at +0)
+    unsigned char *blocks = base + 256;
+    unsigned char *after = blocks + (((size_t)F * kTopM * SLOT + 255) & ~(size_t)255);
+    int *flags = reinterpret_cast<int *>(after);
+    int *list = reinterpret_cast<int *>(after + (((size_t)F * 4 + 255) & ~(size_t)255));
+
+    int cap = t.select_cap ? t.select_cap : (g_env.select_cap ? g_env.select_cap : kSelCapDefault);
+    if (cap < kSelBatch) return PHNMS_ERR_TUNING;
+    if (!(g_env.skip & 1)) {   // (1) the greedy scan over the best-ranked proposals: one warp per frame
+        SelectParams sp;
+        sp.props = props; sp.scores = scores; sp.n_valid = n_valid;
+        sp.F = F; sp.N = (int)N; sp.n_off = n_off; sp.sort_model = sort_model; sp.top_k = (int)top_k; sp.cap = cap;
+        sp.thr = thresh;
+        sp.blocks = blocks; sp.block_bytes = ss.block_bytes;
+        sp.flags = flags; sp.ctrs = ctrs;
+        sp.keep = reinterpret_cast<long long *>(keep);
+        sp.num_keep = reinterpret_cast<long long *>(num_keep);
+        int warps = kSelWarps;
+        while (warps > 1 && select_smem_bytes((int)N, n_off, (int)top_k, warps) > 100 * 1024) warps >>= 1;
+        const size_t sm = select_smem_bytes((int)N, n_off, (int)top_k, warps);
+        {   // (static + dynamic shared memory beyond 48 KB needs the opt-in; cached per device, so simply always)
+            const int e2 = ensure_max_smem(reinterpret_cast<const void *>(phnms_select_kernel), dev.smem_optin);
+            if (e2) return fail_at("select smem attribute", e2);
+        }
+        phnms_select_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(sp);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_at("select launch", (int)e);
+    }
+    if (!(g_env.skip & 2)) {   // (2) every proposal against its frame's kept lanes
+        StreamParams q;
+        q.props = props; q.scores = scores; q.n_valid = n_valid;
+        q.keep = reinterpret_cast<long long *>(keep);
+        q.parent = reinterpret_cast<long long *>(parent);
+        q.blocks = blocks; q.block_bytes = ss.block_bytes;
+        q.flags = flags; q.ctrs = ctrs; q.list = list;
+        q.F = F; q.N = (int)N; q.top_k = (int)top_k; q.sort_model = sort_model; q.thr = thresh;
+        q.ipf = ss.ipf; q.nseg = ss.nseg; q.ips = ss.ips; q.ks = ss.ks;
+        q.off_ring = ss.L.off_ring; q.off_slots = ss.L.off_slots; q.slot_bytes = ss.L.slot_bytes; q.off_bit = ss.L.off_bit;
+        int lanes = t.lanes_per_pass ? t.lanes_per_pass : g_env.lanes_per_pass;
+        if (lanes == 0) lanes = top_k >= 4 ? 4 : (top_k >= 2 ? 2 : 1);
+        if (lanes != 1 && lanes != 2 && lanes != 4) return PHNMS_ERR_TUNING;
+        int rc = 0;
+#define PHNMS_LAUNCH_STREAM(NO, NK)                                                                                   \
+    do {                                                                                                              \
+        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_stream_kernel<NO, NK>), dev.smem_optin);            \
+        if (rc) return fail_at("stream smem attribute", rc);                                                          \
+        phnms_stream_kernel<NO, NK><<<(unsigned)ss.grid, ss.warps * 32, (size_t)ss.L.total, stream>>>(q);             \
+    } while (0)
+        if (n_off == 72) {
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(72, 4);
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(72, 2);
+            else PHNMS_LAUNCH_STREAM(72, 1);
+        } else {
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(36, 4);
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(36, 2);
+            else PHNMS_LAUNCH_STREAM(36, 1);
+        }
+#undef PHNMS_LAUNCH_STREAM
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_at("stream launch", (int)e);
+    }
+    if (N <= cap || (g_env.skip & 4)) return PHNMS_OK;   // every proposal can be drawn: the select kernel never leaves a frame open
+    // (3) resume: frames the select kernel left open AND the streaming pass found unfinished are redone from scratch by the
+    // register-resident cluster kernel (in-kernel candidate selection), working through the device-side list
+    phnms_tuning rt = phnms_tuning{};
+    rt.path = PHNMS_PATH_FUSED;
+    rt.variant = PHNMS_FUSED_REG;
+    rt.max_clusters = t.max_clusters;
+    phnms_plan rp;
+    int rc = make_plan(F, N, n_off, top_k, &rt, &dev, &rp);
+    if (rc != PHNMS_OK) return fail_at("resume plan", rc);
+    if (F > 1) fit_grid_to_occupancy(&rp, F, n_off, &rt);
+    FusedParams fp;
+    fp.props = props; fp.scores = scores; fp.n_valid = n_valid;
+    fp.keep = reinterpret_cast<long long *>(keep);
+    fp.num_keep = reinterpret_cast<long long *>(num_keep);
+    fp.parent = reinterpret_cast<long long *>(parent);
+    fp.F = F; fp.top_k = top_k; fp.N = (int)N; fp.n_off = n_off;
+    fp.rpc = rp.rows_per_cta; fp.csize = rp.cluster; fp.sort_model = sort_model; fp.thr = thresh;
+    fp.L = fused_layout(rp.rows_per_cta, P, rp.cluster);
+    fp.trace = nullptr; fp.trace_len = 0;
+    fp.topm = nullptr; fp.topm_count = 0; fp.claim_ctr = nullptr;
+    fp.frame_list = list; fp.frame_count = ctrs;
+    const FregLayout RL = freg_layout(rp.rows_per_cta, P, rp.cluster);
+    if (n_off == 72) return fail_at("resume launch", launch_cluster(phnms_freg_kernel<72, 1, false, false>, rp, stream, fp, RL));
+    if (rp.cols_per_thread == 1) return fail_at("resume launch", launch_cluster(phnms_freg_kernel<36, 1, false, false>, rp, stream, fp, RL));
+    return fail_at("resume launch", launch_cluster(phnms_freg_kernel<36, 2, false, false>, rp, stream, fp, RL));
 }
 
 static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
@@ -445,9 +682,18 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
     if (rc != 0) return rc;
     if (dev.cc_major != 10) return PHNMS_ERR_DEVICE;
     phnms_plan pl;
-    rc = make_plan(F, N, n_off, tuning, &dev, &pl);
+    phnms_tuning traced;
+    if (trace) {   // the phase trace belongs to the register-resident cluster kernel
+        traced = tuning ? *tuning : phnms_tuning{};
+        if (traced.variant == 0 || traced.variant == PHNMS_FUSED_STREAM) traced.variant = PHNMS_FUSED_REG;
+        tuning = &traced;
+    }
+    rc = make_plan(F, N, n_off, top_k, tuning, &dev, &pl);
     if (rc != PHNMS_OK) return rc;
     if (F > 1) fit_grid_to_occupancy(&pl, F, n_off, tuning);
+    if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_STREAM)
+        return launch_stream(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
+                             tuning, dev, pl, stream);
 
     if (pl.path == PHNMS_PATH_FUSED) {
         FusedParams fp;
@@ -471,6 +717,8 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
         fp.topm = nullptr;
         fp.topm_count = 0;
         fp.claim_ctr = nullptr;
+        fp.frame_list = nullptr;
+        fp.frame_count = nullptr;
         if (pl.variant == PHNMS_FUSED_REG) {
             if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
             unsigned long long *claim_ctr = reinterpret_cast<unsigned long long *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -487,18 +735,15 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
             // costs time in the top-M kernel (one warp per frame) whatever the frame size.  Measured: N = 1000 x 72:
             // 14.9 / 15.6 / 15.4 M frames/s with 8 / 12 / 16; N = 240: 53.9 / 51.4 / 48.1 M.
             int topm_count = (top_k > 0 && top_k <= 4) ? (N > 384 ? 12 : 8) : kTopM;
-            if (const char *ev = getenv("PHNMS_TOPM_COUNT")) {   // experiment knob: candidates per frame (2 .. kTopM)
-                const int v = atoi(ev);
-                if (v >= 2 && v <= kTopM) topm_count = v;
-            }
+            if (g_env.topm_count >= 2 && g_env.topm_count <= kTopM) topm_count = g_env.topm_count;   // experiment knob
             fp.topm_count = topm_count;
             {
                 int warps = kTopmWarps;
                 while (warps > 1 && topm_smem_bytes((int)N, warps) > 160 * 1024) warps >>= 1;
                 const size_t sm = topm_smem_bytes((int)N, warps);
-                if (sm > 48 * 1024) {
-                    cudaError_t e2 = cudaFuncSetAttribute(phnms_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                    if (e2 != cudaSuccess) return (int)e2;
+                {
+                    const int e2 = ensure_max_smem(reinterpret_cast<const void *>(phnms_topm_kernel), dev.smem_optin);
+                    if (e2) return e2;
                 }
                 phnms_topm_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(
                     props, scores, n_valid, F, (int)N, n_off, sort_model, topm_count, thresh, topm, claim_ctr, top_k,
@@ -506,7 +751,7 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
-            fp.topm = getenv("PHNMS_NO_TOPM") ? nullptr : topm;   // debugging aid: force in-kernel candidate selection
+            fp.topm = g_env.no_topm ? nullptr : topm;   // debugging aid: force in-kernel candidate selection
             const FregLayout RL = freg_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
 #define PHNMS_LAUNCH_FREG(TR, DY)                                                                              \
     do {                                                                                                       \

@@ -1,0 +1,274 @@
+// select.cuh -- kernel (1) of the streaming fast path: the greedy scan itself, run on as few proposals as it needs.
+//
+// What it replaces: `scores.sort(0, true)` (libs/ops/csrc/nms.cpp:51) and the serial scan `nms_collect`
+// (libs/ops/csrc/nms_kernel.cu:99-143).  nms_collect walks the sorted order, keeps a proposal iff no earlier KEPT proposal
+// covers it, and stops after top_k kept lanes (:133).  So only a prefix of the order is ever looked at, and a proposal of
+// that prefix only has to be compared with the lanes kept before it.  One warp per frame does exactly that:
+//
+//   repeat:  draw the next kSelBatch proposals in rank order (warp-level select over radix-twiddled keys, ties by index ==
+//            the stable order; <= 32 proposals under the torch sort model: ATen's bitonic network replayed),
+//            fetch their rows, evaluate devIoU (:26-48) of each against the lanes kept so far, then among the survivors,
+//            run the scan over the batch (a survivor is kept iff no kept survivor before it covers it)
+//   until    top_k lanes are kept, or every proposal of the frame was drawn, or `cap` proposals were drawn.
+//
+// Output per frame: a block {nk, open, n} + nk slots {rank key, index, start, end, in-range masks, row} -- byte for byte what
+// phnms_stream_kernel (stream.cuh) evaluates against every proposal of the frame -- plus keep[f, 0..nk) and num_keep[f].
+// A frame is left OPEN when the cap was hit with fewer than top_k lanes kept and proposals left undrawn: if the streaming
+// pass then finds a proposal that no kept lane covers, the frame goes on the resume list (stream.cuh) and is redone by the
+// cluster kernel; if everything is covered (a road with fewer lanes than top_k) the frame is complete as it stands.
+// The cost follows the input: 8 draws for a frame whose first candidates are distinct lanes, up to `cap` draws otherwise.
+#pragma once
+#include "common.cuh"
+#include "fused_reg.cuh"
+
+namespace phnms {
+
+constexpr int kSelWarps = 4;
+constexpr int kSelBatch = 8;       // proposals drawn per batch (one per lane 0..7)
+constexpr int kSelCapDefault = 64; // draws per frame before it is left open
+constexpr int kStreamMaxK = 8;     // kept lanes the streaming path carries per frame (PHNet: max_lanes 4, VIL-100 8)
+constexpr int kBlkHdr = 32;        // bytes: {nk, open, n, 0, 0, 0, 0, 0}
+
+struct SelectParams {
+    const float *props;
+    const float *scores;
+    const int32_t *n_valid;
+    long long F;
+    int N, n_off, sort_model, top_k, cap;
+    float thr;
+    unsigned char *blocks;   // [F] blocks of block_bytes = kBlkHdr + top_k * (kHdr + 4 * round4(5 + n_off))
+    int block_bytes;
+    int *flags;              // [F] "already on the resume list" (cleared here for open frames)
+    unsigned int *ctrs;      // ctrs[0] = length of the resume list (cleared here)
+    long long *keep;
+    long long *num_keep;
+};
+
+__host__ __device__ inline int select_warp_words(int N, int n_off, int top_k) {
+    const int P4 = (5 + n_off + 3) & ~3;
+    const int w = top_k * (8 + P4) + kSelBatch * (P4 | 1) + 2 * kSelBatch + kSelBatch + 32 * (((N + 31) / 32) | 1);
+    return (w + 3) & ~3;
+}
+inline size_t select_smem_bytes(int N, int n_off, int top_k, int warps) {
+    return (size_t)warps * select_warp_words(N, n_off, top_k) * 4;
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) phnms_select_kernel(const SelectParams sp) {
+    extern __shared__ __align__(16) unsigned char smem_sel[];
+    __shared__ float bit_key[kSelWarps][32];
+    __shared__ int bit_val[kSelWarps][32];
+    __shared__ int bit_ok[kSelWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) sp.ctrs[0] = 0u;   // the resume list of this call starts empty
+    const long long f = (long long)blockIdx.x * nw + warp;
+    if (f >= sp.F) return;
+    const int N = sp.N, n_off = sp.n_off, P = 5 + n_off, P4 = (P + 3) & ~3, slot_words = 8 + P4, bp = P4 | 1;
+    const int top_k = sp.top_k;
+    int n = N;
+    if (sp.n_valid) n = max(0, min(sp.n_valid[f], N));
+    const int G = (N + 31) / 32, pitch = G | 1;   // odd pitch: conflict-free both ways
+
+    uint32_t *slots = reinterpret_cast<uint32_t *>(smem_sel) + (size_t)warp * select_warp_words(N, n_off, top_k);
+    float *brow = reinterpret_cast<float *>(slots + top_k * slot_words);   // [kSelBatch][bp] rows of the current batch
+    int *bse = reinterpret_cast<int *>(brow + kSelBatch * bp);              // [kSelBatch][2] their (start, end)
+    uint32_t *adj = reinterpret_cast<uint32_t *>(bse + 2 * kSelBatch);      // [kSelBatch] survivor-vs-survivor hits
+    uint32_t *kb = adj + kSelBatch;                                         // [32][pitch] rank keys, group-major
+
+    const float *sc = sp.scores + (size_t)f * N;
+    const bool bitonic = sp.sort_model == 0 && n <= 32 && n >= 2;
+    u64 sorted = kNone64;   // bitonic: lane j holds the j-th ranked proposal
+    u64 gmin = kNone64;     // select: smallest not-yet-drawn rank key of this lane's group (proposals lane, lane+32, ...)
+
+    if (bitonic) {          // ATen bitonicSortKVInPlace<block_dim_x = 16> (SortUtils.cuh:45-163), see topm.cuh
+        float *bk = bit_key[warp];
+        int *bv = bit_val[warp], *bo = bit_ok[warp];
+        bo[lane] = lane < n;
+        bk[lane] = lane < n ? sc[lane] : 0.0f;
+        bv[lane] = lane < n ? lane : 0;
+        __syncwarp();
+        for (unsigned size = 2; size <= 32; size *= 2) {
+            const bool flag = (size != 32) && ((lane & (size / 2)) != 0);
+            for (unsigned stride = size / 2; stride > 0; stride /= 2) {
+                if (lane < 16) {
+                    const unsigned pa = 2 * lane - (lane & (stride - 1)), pb = pa + stride;
+                    const float ka = bk[pa], kbv = bk[pb];
+                    const int oa = bo[pa], ob = bo[pb];
+                    const bool sw = (gt_nan(ka, kbv) && oa) || !ob;
+                    if (sw == flag) {
+                        const int va = bv[pa], vb = bv[pb];
+                        bk[pa] = kbv; bk[pb] = ka;
+                        bv[pa] = vb; bv[pb] = va;
+                        bo[pa] = ob; bo[pb] = oa;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane < n) sorted = ((u64)(uint32_t)lane << 32) | (uint32_t)bv[lane];  // the sorted position is the rank key
+    } else if (n > 0) {
+        const bool nan_first = sp.sort_model == 1;
+        if (G <= 32) {   // up to 1024 proposals: all score loads are issued before the first one is consumed
+            float sv[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int i = lane + 32 * q;
+                sv[q] = (q < G && i < n) ? sc[i] : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int i = lane + 32 * q;
+                if (q < G) {
+                    uint32_t k = 0xffffffffu;
+                    if (i < n) {
+                        k = key_desc(sv[q], nan_first);
+                        gmin = min(gmin, ((u64)k << 32) | (uint32_t)i);
+                    }
+                    kb[lane * pitch + q] = k;
+                }
+            }
+        } else {
+            for (int q = 0; q < G; ++q) {
+                const int i = lane + 32 * q;
+                uint32_t k = 0xffffffffu;
+                if (i < n) {
+                    k = key_desc(sc[i], nan_first);
+                    gmin = min(gmin, ((u64)k << 32) | (uint32_t)i);
+                }
+                kb[lane * pitch + q] = k;
+            }
+        }
+        __syncwarp();
+    }
+
+    int nk = 0, drawn = 0;
+    bool open = false;
+    while (n > 0) {
+        // ---- draw the next batch in rank order: lane j < nb holds candidate j ------------------------------------
+        u64 myc = kNone64;
+        int nb = 0;
+        if (bitonic) {
+            nb = min(kSelBatch, n - drawn);
+            const u64 v = __shfl_sync(0xffffffffu, sorted, (drawn + lane) & 31);
+            if (lane < nb) myc = v;
+        } else {
+            for (int j = 0; j < kSelBatch; ++j) {
+                const u64 best = warp_min_u64(gmin);
+                if (best == kNone64) break;
+                if (lane == j) myc = best;
+                ++nb;
+                const int g = (int)((uint32_t)best & 31u);       // the group (== lane) that owned the pick
+                u64 cand = kNone64;
+                for (int q = lane; q < G; q += 32) {              // rescan group g: proposal g + 32 q
+                    const int i = g + 32 * q;
+                    const u64 K = ((u64)kb[g * pitch + q] << 32) | (uint32_t)i;
+                    if (i < n && K > best) cand = min(cand, K);
+                }
+                cand = warp_min_u64(cand);
+                if (lane == g) gmin = cand;
+            }
+        }
+        if (nb == 0) break;
+        // ---- their rows: coalesced loads, all issued before the first store ---------------------------------------
+        {
+            float rv[kSelBatch][3];
+#pragma unroll
+            for (int j = 0; j < kSelBatch; ++j) {
+                const u64 kj = __shfl_sync(0xffffffffu, myc, j);
+                const float *row = sp.props + ((size_t)f * N + (j < nb ? (uint32_t)kj : 0u)) * P;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int i = lane + 32 * t;
+                    rv[j][t] = (j < nb && i < P) ? row[i] : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kSelBatch; ++j)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int i = lane + 32 * t;
+                    if (j < nb && i < P4) brow[j * bp + i] = rv[j][t];
+                }
+        }
+        __syncwarp();
+        if (lane < nb) {
+            const int st = lane_start(brow[lane * bp + 2], n_off);       // nms_kernel.cu:29-30
+            bse[2 * lane] = st;
+            bse[2 * lane + 1] = lane_end(brow[lane * bp + 4], st, n_off); // :32-34
+        }
+        if (lane < kSelBatch) adj[lane] = 0u;
+        __syncwarp();
+        // ---- candidates against the lanes kept so far (the mask rows nms_collect would OR into remv, :116-122) ------
+        uint32_t supp = 0u;
+        const int tot = nk * nb;
+        for (int b0 = 0; b0 < tot; b0 += 32) {
+            const int pr = b0 + lane;
+            uint32_t bit = 0u;
+            if (pr < tot) {
+                const int i = pr / nb, j = pr - i * nb;
+                const uint32_t *sl = slots + i * slot_words;
+                if (pair_hit_scalar(reinterpret_cast<const float *>(sl + 8), brow + j * bp, (int)sl[2], (int)sl[3], bse[2 * j],
+                                    bse[2 * j + 1], sp.thr))
+                    bit = 1u << j;
+            }
+            supp |= __reduce_or_sync(0xffffffffu, bit);
+        }
+        const uint32_t surv = ~supp & ((1u << nb) - 1u);
+        // ---- survivors against each other (strict upper triangle in rank order, :85-87), then the scan over the batch ------
+        const int s = __popc(surv), need = top_k - nk;
+        if (s >= 2 && need >= 2) {
+            const int np = s * (s - 1) / 2;   // <= 28
+            if (lane < np) {
+                int ia = 0, rem = lane;
+                while (rem >= s - 1 - ia) { rem -= s - 1 - ia; ++ia; }
+                const int ib = ia + 1 + rem;
+                const int a = (int)__fns(surv, 0, ia + 1), b = (int)__fns(surv, 0, ib + 1);
+                if (pair_hit_scalar(brow + a * bp, brow + b * bp, bse[2 * a], bse[2 * a + 1], bse[2 * b], bse[2 * b + 1], sp.thr))
+                    atomicOr(&adj[a], 1u << b);
+            }
+            __syncwarp();
+        }
+        uint32_t alive = surv;
+        while (alive && nk < top_k) {
+            const int a = __ffs(alive) - 1;
+            alive &= ~(1u << a);
+            alive &= ~adj[a];
+            const u64 Ka = __shfl_sync(0xffffffffu, myc, a);
+            uint32_t *sl = slots + nk * slot_words;
+            for (int i = lane; i < P4; i += 32) sl[8 + i] = __float_as_uint(brow[a * bp + i]);
+            if (lane == 0) {
+                const int st = bse[2 * a], en = bse[2 * a + 1];
+                uint32_t m[3];
+                range_mask<3>(st, en, m);
+                sl[0] = (uint32_t)(Ka >> 32); sl[1] = (uint32_t)Ka; sl[2] = (uint32_t)st; sl[3] = (uint32_t)en;
+                sl[4] = m[0]; sl[5] = m[1]; sl[6] = m[2]; sl[7] = 0u;
+                sp.keep[(size_t)f * N + nk] = (long long)(uint32_t)Ka;   // :118
+            }
+            ++nk;
+        }
+        __syncwarp();
+        drawn += nb;
+        if (nk == top_k || drawn >= n) break;   // :133 / every proposal of the frame was drawn
+        if (drawn >= sp.cap) {
+            open = true;
+            break;
+        }
+    }
+
+    // ---- the frame's block: header + nk slots, 16-byte stores --------------------------------------------------------------
+    unsigned char *blk = sp.blocks + (size_t)f * sp.block_bytes;
+    if (lane < 2) {
+        const uint4 h = lane == 0 ? make_uint4((uint32_t)nk, open ? 1u : 0u, (uint32_t)n, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(blk)[lane] = h;
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(slots);
+        uint4 *dst = reinterpret_cast<uint4 *>(blk + kBlkHdr);
+        for (int i = lane; i < nk * slot_words / 4; i += 32) dst[i] = src[i];
+    }
+    if (lane == 0) {
+        sp.num_keep[f] = (long long)nk;   // :142 (nk <= top_k)
+        if (open) sp.flags[f] = 0;
+    }
+}
+
+}  // namespace phnms

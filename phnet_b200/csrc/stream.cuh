@@ -1,0 +1,376 @@
+// stream.cuh -- kernel (2)+(3) of the streaming fast path: every proposal of every frame against the frame's kept lanes.
+//
+// phnms_select_kernel (select.cuh) has already run the greedy scan (nms_collect, libs/ops/csrc/nms_kernel.cu:99-143) and
+// knows the kept lanes of each frame.  What is left of the reference's work is the part that touches all the data: the
+// mask rows of the kept lanes (nms_kernel, :50-96, of which nms_collect only ever reads the rows of kept lanes, :116-122)
+// and the parent stamps (:123-129).  With the kept lanes known up front that is a pure streaming map over proposals:
+//
+//     parent[j] = 1 + max{ k : kept lane k is ranked before j and devIoU(kept_k, j) }   (or k + 1 if j IS kept lane k)
+//
+// No cluster, no per-frame barrier, no exchange: the unit of work is a 32-row ITEM owned by one warp.
+//   * each warp owns a private staging slot in shared memory and feeds it itself: one TMA 1-D bulk copy (UBLKCP) of the
+//     item's 16-byte aligned body + 4-byte cp.async (LDGSTS) for <= 3 unaligned words at either end and for the 32 scores,
+//     all completing on the warp's own mbarrier (cp.async.mbarrier.arrive.noinc);
+//   * as soon as the rows are in REGISTERS (one proposal per thread, 72 offsets) the slot is free and the warp requests its
+//     next item, which lands while the current one is evaluated -- 16 warps per SM = 16 independent load streams, ~160 KB
+//     in flight per SM, and the phases of different warps overlap instead of running in lock step;
+//   * the kept lanes of a frame (block written by the select kernel) are shared by the CTA through a small ring of
+//     shared-memory slots with full / empty mbarriers; whichever warp first needs a block claims the request (atomicCAS);
+//   * evaluation: freg_eval_multi (fused_reg.cuh) -- NKP kept lanes per pass over the registers, each chain the reference's
+//     ascending sequential fp32 sum (:38-44), packed FADD2 subtractions, R2P predicates; negative common starts (header
+//     words / the wrapped unsigned-char counter, :38) take the exact one-lane evaluator.
+//   * an OPEN frame (select hit its draw cap) that still has a proposal no kept lane covers is appended to the resume list.
+// Roofline: HBM (rows + scores read once, parent / keep padding written once; the kept blocks are L2 hits).
+#pragma once
+#include "common.cuh"
+#include "fused_reg.cuh"
+#include "select.cuh"
+
+namespace phnms {
+
+constexpr int kStreamMaxWarps = 16;
+constexpr int kStreamMaxRing = 32;
+
+struct StreamParams {
+    const float *props;
+    const float *scores;
+    const int32_t *n_valid;
+    long long *keep;
+    long long *parent;
+    const unsigned char *blocks;
+    int block_bytes;
+    int *flags;
+    unsigned int *ctrs;
+    int *list;
+    long long F;
+    int N, top_k, sort_model;
+    float thr;
+    int ipf;    // 32-row items per frame: ceil(N / 32)
+    int nseg;   // a frame is cut into nseg units of ips item slots (nseg > 1 only when there are fewer frames than CTAs)
+    int ips;
+    int ks;     // kept-block ring slots
+    int off_ring, off_slots, slot_bytes, off_bit;
+};
+
+struct StreamLayout {
+    int off_ring, off_slots, slot_bytes, off_bit, total;
+};
+
+// shared memory: [0,128) row mbarriers (one per warp) | [128,384) kfull | [384,640) kempty | [640] request ticket
+__host__ __device__ inline StreamLayout stream_layout(int warps, int P, int block_bytes, int ks) {
+    StreamLayout L;
+    int o = 768;
+    L.off_ring = o;
+    o += ks * block_bytes;
+    o = (o + 127) & ~127;
+    L.off_slots = o;
+    L.slot_bytes = 128 + ((16 + 32 * P * 4 + 16 + 127) & ~127);   // 32 scores | rows (16 B lead for the alignment shift)
+    o += warps * L.slot_bytes;
+    L.off_bit = o;
+    o += warps * 384;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// devIoU (nms_kernel.cu:26-48) of NK kept lanes -- consecutive slots starting at shared address s0 -- against this thread's
+// proposal, in ONE pass over its registers: NK independent fp32 chains, each the reference's ascending sequential sum
+// (:38-44).  Row word i of kept lane k enters the sum iff bit i of (ma_k & mb) is set: the pair's range
+// [max(sa, sb), min(ea, eb)] is the intersection of the two lanes' own ranges -- which needs max(sa, sb) >= 0 (below, header
+// words or the wrapped unsigned-char counter come into play, :38): if any active pair of the warp has a negative start the
+// function returns false and the caller takes the exact one-lane evaluator (freg_eval).  All addresses are one register +
+// immediates; what stays live across the pass is dist / limit per lane and one word of flags.
+template <int NOFF, int NK>
+__device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, bool live, u64 myK, int st, int en,
+                                            const uint32_t (&mb)[(5 + NOFF + 31) / 32], const float (&x)[NOFF], float thr,
+                                            uint32_t &par, int k0) {
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4;
+    float lim[NK], dist[NK];
+    uint32_t self = 0u;
+    bool rare = false;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const uint4 wh = lds_u4(s0 + k * SLOT);
+        const u64 wk = k < cnt ? (((u64)wh.x << 32) | wh.y) : kNone64;   // a padding lane activates nobody
+        const int sa = (int)wh.z, ea = (int)wh.w;
+        const int start = max(sa, st), end = min(ea, en);                 // :31,:34 (both ends clamped to NOFF-1)
+        const bool act = live && (myK > wk) && (end >= start);            // ranked after the kept lane; :36
+        rare |= act && (start < 0);
+        const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
+        lim[k] = act ? __fmul_rn(thr, (float)len) : -__int_as_float(0x7f800000);   // :46; -inf: never a hit
+        if (myK == wk) self |= 1u << k;
+        dist[k] = 0.0f;
+    }
+    if (__any_sync(0xffffffffu, rare)) return false;
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        uint32_t m[NK];   // pair masks of this 32-word span
+#pragma unroll
+        for (int k = 0; k < NK; ++k) m[k] = lds_u32(s0 + k * SLOT + 16 + 4 * w) & mb[w];
+#pragma unroll
+        for (int g = 8 * w; g < 8 * w + 8; ++g) {
+            if (g >= 1 && g < P4 / 4) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const float4 av = lds_v4(s0 + k * SLOT + kHdr + 16 * g);
+                    const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u += 2) {
+                        const int i = 4 * g + u;
+                        const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
+                        float t0 = 0.0f, t1 = 0.0f;
+                        if (v0 && v1) {
+                            fsub2(a4[u], a4[u + 1], x[v0 ? i - 5 : 0], x[v1 ? i - 4 : 0], t0, t1);
+                        } else {
+                            if (v0) t0 = __fsub_rn(a4[u], x[v0 ? i - 5 : 0]);
+                            if (v1) t1 = __fsub_rn(a4[u + 1], x[v1 ? i - 4 : 0]);
+                        }
+                        if (v0 && (m[k] & (1u << (i & 31)))) dist[k] = __fadd_rn(dist[k], fabsf(t0));
+                        if (v1 && (m[k] & (1u << ((i + 1) & 31)))) dist[k] = __fadd_rn(dist[k], fabsf(t1));
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k)      // in keep order: the last kept lane that covers a proposal wins (:127)
+        if (k < cnt && ((dist[k] < lim[k]) || ((self >> k) & 1u))) par = (uint32_t)(k0 + k + 1);   // :46,:127,:129
+    return true;
+}
+
+template <int NOFF, int NKP>
+__global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(const StreamParams sp) {
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t bar_rows = smem_u32(smem) + 8u * warp;
+    const uint32_t kfull0 = smem_u32(smem) + 128u, kempty0 = smem_u32(smem) + 384u;
+    uint32_t *next_req = reinterpret_cast<uint32_t *>(smem + 640);
+    unsigned char *ring = smem + sp.off_ring;
+    unsigned char *myslot = smem + sp.off_slots + (size_t)warp * sp.slot_bytes;
+    float *sc_buf = reinterpret_cast<float *>(myslot);
+    unsigned char *rows_base = myslot + 128;
+    const int ks = sp.ks, ips = sp.ips, nseg = sp.nseg;
+
+    if (tid == 0) {
+        for (int w = 0; w < nwarps; ++w) mbar_init(smem_u32(smem) + 8u * w, 33);   // 1 expect_tx arrive + 32 cp.async arrives
+        for (int s = 0; s < ks; ++s) {
+            mbar_init(kfull0 + 8u * s, 1);
+            mbar_init(kempty0 + 8u * s, (uint32_t)ips);   // one arrive per item slot of the unit
+        }
+        *next_req = 0u;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // units of this CTA: u = b, b + G, ...; unit u = (frame u / nseg, segment u % nseg); item slots m = us * ips + ci
+    const long long U = sp.F * nseg;
+    const uint32_t b = blockIdx.x, G = gridDim.x;
+    const uint32_t nu = b < U ? (uint32_t)((U - b + G - 1) / G) : 0u;
+    const uint32_t M = nu * (uint32_t)ips;   // (the host keeps this below 2^31)
+    const int look = ks - 2;
+    if (M == 0u) return;
+
+    struct Item { long long f; int r0, nrows, us; bool valid; };
+    auto decode = [&](uint32_t m) {
+        Item it;
+        const uint32_t us = m / (uint32_t)ips;
+        const int ci = (int)(m - us * (uint32_t)ips);
+        const long long u = (long long)b + (long long)us * G;
+        it.f = nseg == 1 ? u : u / nseg;
+        const int sg = (int)(u - it.f * nseg);
+        const int c = sg * ips + ci;
+        it.valid = c < sp.ipf;
+        it.r0 = c * 32;
+        it.us = (int)us;
+        int nv = sp.N;
+        if (sp.n_valid) nv = max(0, min(sp.n_valid[it.f], sp.N));
+        it.nrows = it.valid ? max(0, min(nv - it.r0, 32)) : 0;
+        return it;
+    };
+    // the item's rows -> this warp's slot.  Row data keeps its global address modulo 16 (rows are only 4-byte aligned:
+    // 308 / 164 bytes), so the aligned body is one bulk copy and at most 3 words at either end are copied singly.
+    auto issue = [&](const Item &it) {
+        if (it.nrows <= 0) return;
+        const float *src = sp.props + ((size_t)it.f * sp.N + it.r0) * P;
+        const uintptr_t a0 = (uintptr_t)src, bytes = (uintptr_t)it.nrows * P * 4;
+        const uintptr_t b0 = (a0 + 15) & ~(uintptr_t)15, e0 = (a0 + bytes) & ~(uintptr_t)15;
+        unsigned char *D = rows_base + (a0 & 15);
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_rows, (uint32_t)(e0 - b0));
+            bulk_g2s(smem_u32(D + (b0 - a0)), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
+        }
+        const int hw = (int)((b0 - a0) >> 2), tw = (int)((a0 + bytes - e0) >> 2), t0 = (int)((e0 - a0) >> 2);
+        if (lane >= 1 && lane - 1 < hw) cp_async_4(smem_u32(D + 4 * (lane - 1)), src + (lane - 1));
+        if (lane >= 4 && lane - 4 < tw) cp_async_4(smem_u32(D + 4 * (t0 + lane - 4)), src + t0 + (lane - 4));
+        if (lane < it.nrows) cp_async_4(smem_u32(sc_buf + lane), sp.scores + (size_t)it.f * sp.N + it.r0 + lane);
+        cp_async_mbar_arrive_noinc(bar_rows);
+    };
+    // kept blocks: requested up to `look` units ahead by whichever warp gets there first (lane 0 only)
+    auto ensure_requested = [&](long long upto) {
+        for (;;) {
+            const uint32_t t = *reinterpret_cast<volatile uint32_t *>(next_req);
+            if ((long long)t > upto || t >= nu) break;
+            if (atomicCAS(next_req, t, t + 1u) != t) continue;
+            const uint32_t slot = t % (uint32_t)ks, use = t / (uint32_t)ks;
+            if (use > 0u) mbar_wait(kempty0 + 8u * slot, (use - 1u) & 1u);   // every item slot of the previous user is done
+            const long long uq = (long long)b + (long long)t * G;
+            const long long fq = nseg == 1 ? uq : uq / nseg;
+            mbar_arrive_expect_tx(kfull0 + 8u * slot, (uint32_t)sp.block_bytes);
+            bulk_g2s(smem_u32(ring + (size_t)slot * sp.block_bytes), sp.blocks + (size_t)fq * sp.block_bytes,
+                     (uint32_t)sp.block_bytes, kfull0 + 8u * slot);
+        }
+    };
+
+    uint32_t rphase = 0u;
+    uint32_t m = (uint32_t)warp;
+    if (m < M) {
+        const Item first = decode(m);
+        issue(first);
+        if (lane == 0) ensure_requested((long long)first.us + look);
+    }
+
+    for (; m < M; m += (uint32_t)nwarps) {
+        float x[NOFF];
+        int st, en, i_out, nrows;
+        float score = 0.0f;
+        long long f;
+        uint32_t kslot, kpar;
+        bool valid;
+        {
+            const Item cur = decode(m);
+            f = cur.f;
+            nrows = cur.nrows;
+            valid = cur.valid;
+            i_out = cur.r0 + lane;
+            kslot = (uint32_t)cur.us % (uint32_t)ks;
+            kpar = ((uint32_t)cur.us / (uint32_t)ks) & 1u;
+            if (nrows > 0) {
+                mbar_wait(bar_rows, rphase);
+                rphase ^= 1u;
+                const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)f * sp.N + cur.r0) * P);
+                const float *row = reinterpret_cast<const float *>(rows_base + (a0 & 15)) + (size_t)(lane < nrows ? lane : 0) * P;
+#pragma unroll
+                for (int i = 0; i < NOFF; ++i) x[i] = row[5 + i];
+                st = lane_start(row[2], NOFF);       // nms_kernel.cu:29-30
+                en = lane_end(row[4], st, NOFF);     // :32-34
+                score = sc_buf[lane < nrows ? lane : 0];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NOFF; ++i) x[i] = 0.0f;
+                st = 0;
+                en = -1;
+            }
+            __syncwarp();   // every lane has read its row: the slot is free for the next item
+            if (m + (uint32_t)nwarps < M) issue(decode(m + (uint32_t)nwarps));
+            if (lane == 0) ensure_requested((long long)cur.us + look);
+            __syncwarp();
+        }
+
+        // ---- the frame's kept lanes (block written by the select kernel: {nk, open, n} + slots) -------------------------------
+        mbar_wait(kfull0 + 8u * kslot, kpar);
+        const uint32_t blk_s = smem_u32(ring) + kslot * (uint32_t)sp.block_bytes;
+        const int nk = min((int)lds_u32(blk_s), sp.top_k);
+        const bool open = lds_u32(blk_s + 4) != 0u;
+        const int nvf = (int)lds_u32(blk_s + 8);   // proposals in the frame
+
+        const bool real = lane < nrows;
+        uint32_t key = key_desc(real ? score : 0.0f, sp.sort_model == 1);
+        // (torch sort model) a frame of <= 32 proposals is ordered by ATen's unstable bitonic network -- the select kernel's
+        // rank keys are then the sorted positions, and so must these be; such a frame is exactly one item (rows 0 .. n-1)
+        if (sp.sort_model == 0 && valid && nvf <= 32 && nvf >= 2 && nrows > 0) {
+            const int nv = nvf;
+            {
+                float *bit_key = reinterpret_cast<float *>(smem + sp.off_bit + warp * 384);
+                int *bit_val = reinterpret_cast<int *>(bit_key + 32), *bit_ok = bit_val + 32;
+                bit_ok[lane] = lane < nv;
+                bit_key[lane] = lane < nv ? score : 0.0f;
+                bit_val[lane] = lane < nv ? lane : 0;
+                __syncwarp();
+                for (unsigned size = 2; size <= 32; size *= 2) {
+                    const bool flag = (size != 32) && ((lane & (size / 2)) != 0);
+                    for (unsigned stride = size / 2; stride > 0; stride /= 2) {
+                        if (lane < 16) {
+                            const unsigned pa = 2 * lane - (lane & (stride - 1)), pb = pa + stride;
+                            const float ka = bit_key[pa], kb = bit_key[pb];
+                            const int oa = bit_ok[pa], ob = bit_ok[pb];
+                            const bool sw = (gt_nan(ka, kb) && oa) || !ob;
+                            if (sw == flag) {
+                                const int va = bit_val[pa], vb = bit_val[pb];
+                                bit_key[pa] = kb; bit_key[pb] = ka;
+                                bit_val[pa] = vb; bit_val[pb] = va;
+                                bit_ok[pa] = ob;  bit_ok[pb] = oa;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                int mypos = 0;
+                for (int q = 0; q < 32; ++q)
+                    if (bit_val[q] == lane && q < nv) mypos = q;
+                key = (uint32_t)mypos;
+                __syncwarp();
+            }
+        }
+        const u64 myK = real ? (((u64)key << 32) | (uint32_t)i_out) : kNone64;
+        uint32_t mb[MW], par = 0u;
+        range_mask<MW>(st, en, mb);
+
+        if (valid) {
+            if (nrows > 0) {
+                for (int k0 = 0; k0 < nk; k0 += NKP) {
+                    const int cnt = min(NKP, nk - k0);
+                    if (!stream_eval<NOFF, NKP>(blk_s + kBlkHdr + (uint32_t)k0 * SLOT, cnt, real, myK, st, en, mb, x, sp.thr, par, k0)) {
+                        // a pair with a negative common start somewhere in the warp: the exact evaluator, one lane at a time
+                        FusedParams fp;
+                        fp.thr = sp.thr;
+                        auto my_hdr = [&](int) { return sp.props + ((size_t)f * sp.N + (uint32_t)i_out) * P; };
+                        const bool live1[1] = {real};
+                        const u64 myK1[1] = {myK};
+                        const int st1[1] = {st}, en1[1] = {en};
+                        uint32_t mb1[1][MW], par1[1] = {par};
+#pragma unroll
+                        for (int w = 0; w < MW; ++w) mb1[0][w] = mb[w];
+                        for (int k = 0; k < cnt; ++k) {
+                            const unsigned char *const h1[1] = {ring + (size_t)kslot * sp.block_bytes + kBlkHdr + (size_t)(k0 + k) * SLOT};
+                            bool hit[1][1];
+                            freg_eval<NOFF, 1, 1>(fp, f, h1, live1, myK1, st1, en1, mb1, reinterpret_cast<const float (&)[1][NOFF]>(x),
+                                                  my_hdr, par1, hit, k0 + k);
+                        }
+                        par = par1[0];
+                    }
+                }
+            }
+            // ---- outputs, written once ------------------------------------------------------------------------------------
+            if (i_out < sp.N) {
+                st_global_cs_u64(sp.parent + (size_t)f * sp.N + i_out, (long long)par);
+                if (i_out >= nk) st_global_cs_u64(sp.keep + (size_t)f * sp.N + i_out, 0ll);   // :139-140
+            }
+            // an open frame with a proposal nobody covers has more lanes to keep than the select kernel looked for
+            if (open && __any_sync(0xffffffffu, real && par == 0u)) {
+                if (lane == 0 && atomicExch(sp.flags + f, 1) == 0) sp.list[atomicAdd(sp.ctrs, 1u)] = (int)f;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kempty0 + 8u * kslot);
+    }
+}
+
+}  // namespace phnms

@@ -60,7 +60,7 @@ _ws_cache: dict = {}           # (device index, stream handle) -> reusable works
 
 
 def _workspace(L, dev, stream, F, N, n_off, t, tp):
-    key = (F, N, n_off, None if t is None else (t.path, t.cluster, t.threads, t.max_clusters, t.variant, t.schedule))
+    key = (F, N, n_off, None if t is None else t.key())
     nbytes = _ws_bytes_cache.get(key)
     if nbytes is None:
         nbytes = _ws_bytes_cache[key] = int(L.phnms_workspace_bytes(F, N, n_off, tp))
@@ -199,7 +199,7 @@ def sort_order(scores: torch.Tensor, n_valid: torch.Tensor | None = None, *, sor
     return order[0] if one else order
 
 
-def plan(F: int, N: int, n_off: int, tuning=None) -> dict:
-    """What one call would launch for this shape (path, cluster size, threads, shared memory, grid)."""
+def plan(F: int, N: int, n_off: int, tuning=None, top_k: int = -1) -> dict:
+    """What one call would launch for this shape (path, variant, threads, shared memory, grid); top_k < 0: PHNet's 1..8."""
     t = tuning if isinstance(tuning, _capi.Tuning) or tuning is None else _capi.tuning(**tuning)
-    return _capi.plan(F, N, n_off, t)
+    return _capi.plan(F, N, n_off, t, top_k)

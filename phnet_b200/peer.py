@@ -104,7 +104,8 @@ class PeerCollector:
         return int(self._mem[(self.flag_off + 8 * _capi.MAX_DST) // 8].item()) & 0xffffffff
 
     def collect_arg(self, buf: int) -> _capi.Collect:
-        return _capi.collect([b + buf * self.buf_bytes for b in self.base], row0=self.rank * self.rows)
+        return _capi.collect([b + buf * self.buf_bytes for b in self.base], rows=self.world * self.rows, width=self.width,
+                             row0=self.rank * self.rows)
 
     # -- completion flags ----------------------------------------------------------------------------------------
     def _sync(self, signal_epoch: int, wait_epoch: int, timeout_s: float):
@@ -142,4 +143,6 @@ def local_collect(tensors, row0: int = 0) -> _capi.Collect:
     for t in tensors:
         if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.dim() == 2):
             raise RuntimeError("collection buffers must be contiguous int64 CUDA tensors [rows, top_k + 1]")
-    return _capi.collect([t.data_ptr() for t in tensors], row0=row0)
+    if len({tuple(t.shape) for t in tensors}) != 1:
+        raise RuntimeError("collection buffers must all have the same shape")
+    return _capi.collect([t.data_ptr() for t in tensors], rows=tensors[0].shape[0], width=tensors[0].shape[1], row0=row0)

@@ -1,4 +1,6 @@
-"""Small deterministic program for ncu: a few launches of the lane-NMS op on one shape (env: N NOFF F TOPK CLUSTER THREADS PATH REPS)."""
+"""Small deterministic program for ncu: a few launches of the lane-NMS op on one shape.
+env: N NOFF F TOPK GROUPS OUTL REPS and TUNE (a JSON tuning dict, e.g. '{"lanes_per_pass":2}')."""
+import json
 import os
 import sys
 
@@ -10,13 +12,13 @@ from phnet_b200.ops import nms_batched  # noqa: E402
 
 N = int(os.environ.get("N", 1000)); n_off = int(os.environ.get("NOFF", 72)); F = int(os.environ.get("F", 2368))
 top_k = int(os.environ.get("TOPK", 4)); reps = int(os.environ.get("REPS", 4))
-tune = _capi.tuning(path=int(os.environ.get("PATH_", 0)), cluster=int(os.environ.get("CLUSTER", 0)),
-                    threads=int(os.environ.get("THREADS", 0)))
+groups = int(os.environ.get("GROUPS", 8)); outl = float(os.environ.get("OUTL", 0.1))
+tune = _capi.tuning(**json.loads(os.environ["TUNE"])) if os.environ.get("TUNE") else None
 dev = torch.device("cuda:0")
-props, scores = synth.make_frames_chunked(F, N, n_off, seed=0, device=dev)
+props, scores = synth.make_frames_chunked(F, N, n_off, seed=0, device=dev, groups=groups, outlier_frac=outl)
 out = (torch.empty((F, N), dtype=torch.int64, device=dev), torch.empty((F,), dtype=torch.int64, device=dev),
        torch.empty((F, N), dtype=torch.int64, device=dev))
 for _ in range(reps):
     nms_batched(props, scores, 50.0, top_k, tuning=tune, out=out)
 torch.cuda.synchronize()
-print("plan", _capi.plan(F, N, n_off, tune), "kept", out[1][:8].tolist())
+print("plan", _capi.plan(F, N, n_off, tune, top_k), "kept", out[1][:8].tolist())

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == set(_capi.EXPORTS), "include/phnms.h and the ctypes binding disagree"
     for s in syms:
         assert hasattr(L, s), f"libphnms.so does not export {s}"
-    assert L.phnms_abi_version() == _capi.ABI_VERSION == 4
+    assert L.phnms_abi_version() == _capi.ABI_VERSION == 5
 
 
 def test_library_is_sm100a_only_and_has_tma_and_cluster_code():
@@ -40,10 +40,14 @@ def test_library_is_sm100a_only_and_has_tma_and_cluster_code():
     checked = 0
     for fn in funcs:
         name = fn.split("\n", 1)[0]
-        if any(k in name for k in ("freg_kernel", "fused_kernel", "mask_kernel")):
+        if any(k in name for k in ("freg_kernel", "fused_kernel", "mask_kernel", "stream_kernel", "select_kernel")):
             assert "FFMA" not in fn, name
             checked += 1
-    assert checked >= 5
+            if "stream_kernel" in name:     # the streaming kernel: TMA bulk copies, cp.async on an mbarrier, packed fp32 subtraction
+                assert "UBLKCP" in fn and "LDGSTS" in fn and "SYNCS" in fn, name
+                if "ELi1EEE" not in name:
+                    assert "FADD2" in fn, name
+    assert checked >= 12
 
 
 def test_error_strings_and_argument_checks_without_a_gpu():
@@ -69,9 +73,17 @@ def test_error_strings_and_argument_checks_without_a_gpu():
     assert L.phnms_forward_collect_f32(*args, ctypes.byref(c)) == -1
     c.n_dst = _capi.MAX_DST + 1
     assert L.phnms_forward_collect_f32(*args, ctypes.byref(c)) == -1
-    c = _capi.collect([4096])
+    c = _capi.collect([4096], rows=1, width=5)
     assert L.phnms_forward_collect_f32(*(args[:7] + (0,) + args[8:]), ctypes.byref(c)) == -1       # top_k == 0
-    assert L.phnms_forward_collect_f32(*args, ctypes.byref(_capi.collect([4100]))) == -1            # not 8-byte aligned
+    assert L.phnms_forward_collect_f32(*args, ctypes.byref(_capi.collect([4100], rows=1, width=5))) == -1   # not 8-byte aligned
+    # a record is never stored outside a destination: width must be top_k + 1 and row0 + F must fit (checked before any launch;
+    # with valid descriptors the same null-pointer call gets as far as the shape / pointer checks: -1 either way, so compare
+    # against a descriptor that is fine and a shape that is not)
+    bad_shape = args[:5] + (0,) + args[6:]       # n_off == 0 -> -2, but only if the descriptor passed
+    assert L.phnms_forward_collect_f32(*bad_shape, ctypes.byref(_capi.collect([4096], rows=1, width=5))) == -2
+    assert L.phnms_forward_collect_f32(*bad_shape, ctypes.byref(_capi.collect([4096], rows=1, width=4))) == -1   # width != top_k + 1
+    assert L.phnms_forward_collect_f32(*bad_shape, ctypes.byref(_capi.collect([4096], rows=1, width=5, row0=1))) == -1   # row0 + F > rows
+    assert L.phnms_forward_collect_f32(*bad_shape, ctypes.byref(_capi.collect([4096], rows=0, width=5))) == -1
     assert L.phnms_peer_sync(None, nul, 0, 1, 1, 0, nul, nul) == -1
     assert L.phnms_peer_sync(None, nul, 2, 0, 0, 0, nul, nul) == 0                                  # nothing to do
     assert L.phnms_peer_open(None, None) == -1 and L.phnms_peer_close(None) == -1 and L.phnms_peer_free(None) == -1
@@ -80,11 +92,24 @@ def test_error_strings_and_argument_checks_without_a_gpu():
 
 
 def test_plans():
-    p = _capi.plan(16384, 1000, 72)
-    assert p["path"] == _capi.PATH_FUSED and p["cluster"] * p["rows_per_cta"] >= 1000
-    assert p["smem_bytes"] <= 232448 and p["grid"] % p["cluster"] == 0 and p["launches"] == 2
-    assert p["workspace_bytes"] == 16384 * 16 * (32 + 4 * 80) + 512   # claim counter + per-frame block of up to 16 candidate slots
-    assert _capi.plan(1, 240, 72)["cluster"] == 1                       # the real OpenLane-V shape fits one CTA
+    p = _capi.plan(16384, 1000, 72)             # the headline shape: select + stream (+ resume) kernels, one CTA per SM
+    assert p["path"] == _capi.PATH_FUSED and p["variant"] == _capi.FUSED_STREAM and p["launches"] == 3
+    assert p["cluster"] == 1 and p["threads"] == 512 and p["grid"] == 148 and p["smem_bytes"] <= 232448
+    ws = 16384 * 16 * (32 + 4 * 80)             # per-frame block (capacity of the cluster kernel's 16 candidate slots)
+    assert ws < p["workspace_bytes"] <= ws + 2 * 16384 * 4 + 2048
+    for top_k in (0, 9, 1000):                  # outside [1, 8]: the register-resident cluster kernel
+        q = _capi.plan(16384, 1000, 72, None, top_k)
+        assert q["variant"] == _capi.FUSED_REG and q["cluster"] * q["rows_per_cta"] >= 1000 and q["launches"] == 2
+        assert q["grid"] % q["cluster"] == 0 and q["workspace_bytes"] == p["workspace_bytes"]
+    assert _capi.plan(16384, 1000, 72, None, 8)["variant"] == _capi.FUSED_STREAM
+    assert _capi.plan(1, 240, 72, _capi.tuning(variant=_capi.FUSED_REG))["cluster"] == 1   # the real OpenLane-V shape fits one CTA
+    assert _capi.plan(4, 100, 50)["variant"] == _capi.FUSED_SMEM        # other offset counts: shared-memory cluster kernel
+    with pytest.raises(_capi.PhnmsError):
+        _capi.plan(4, 100, 50, _capi.tuning(variant=_capi.FUSED_STREAM))
+    with pytest.raises(_capi.PhnmsError):
+        _capi.plan(4, 1000, 72, _capi.tuning(variant=_capi.FUSED_STREAM), 0)
+    small = _capi.plan(2, 1000, 72)             # fewer frames than SMs: frames are cut into units so that every SM has work
+    assert small["variant"] == _capi.FUSED_STREAM and small["grid"] > 2
     assert _capi.plan(1, 8192, 72)["path"] == _capi.PATH_FUSED          # the whole stress sweep stays on the fused path
     big = _capi.plan(1, 40000, 72)
     assert big["path"] == _capi.PATH_TILED and big["launches"] == 3 and big["workspace_bytes"] > 0
@@ -136,5 +161,5 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     ver, rc, cluster, threads, ws = out.stdout.split()
-    assert int(ver) == _capi.ABI_VERSION and int(rc) == 0 and int(cluster) == 2 and int(threads) == 512 and int(ws) > 0
+    assert int(ver) == _capi.ABI_VERSION and int(rc) == 0 and int(cluster) == 1 and int(threads) == 512 and int(ws) > 0
     subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-x", "c++", os.path.join(inc, "phnms.h")], check=True)
