@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace phnms {
 
@@ -180,7 +181,15 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
         for (int i = 0; i < 64; ++i)
             if (mbar_try_wait(bar, parity)) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > kMbarTimeoutNs) __trap();
+        if (now - t0 > kMbarTimeoutNs) {
+#ifdef PHNMS_WAIT_PRINT   // debugging build: say who waited on what and carry on (results are wrong, the launch terminates)
+            printf("phnms: mbarrier wait timed out: block %d thread %d barrier@%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+                   bar, parity);
+            return;
+#else
+            __trap();
+#endif
+        }
     }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

@@ -79,7 +79,7 @@ int ensure_max_smem(const void *kern, int smem_optin) {
 
 // experiment knobs of debug sessions, read once at load (never on the call path)
 struct EnvKnobs {
-    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, no_stream, debug, skip;
+    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, debug, skip;
     EnvKnobs() {
         auto geti = [](const char *n) { const char *v = getenv(n); return v ? atoi(v) : 0; };
         topm_count = geti("PHNMS_TOPM_COUNT");
@@ -87,6 +87,7 @@ struct EnvKnobs {
         select_cap = geti("PHNMS_SELECT_CAP");
         lanes_per_pass = geti("PHNMS_LANES_PER_PASS");
         stream_warps = geti("PHNMS_STREAM_WARPS");
+        stream_cpt = geti("PHNMS_STREAM_CPT");
         no_stream = getenv("PHNMS_NO_STREAM") != nullptr;
         debug = getenv("PHNMS_DEBUG") != nullptr;
         skip = geti("PHNMS_SKIP");   // timing experiments only (results are wrong): 1 = no select, 2 = no stream, 4 = no resume
@@ -116,7 +117,7 @@ size_t tiled_workspace(int64_t F, int64_t N) {
 // Launch shape of the streaming kernel (stream.cuh): warps per CTA, how frames are cut into units when there are fewer
 // frames than SMs, the kept-block ring, the grid (one persistent CTA per SM).
 struct StreamShape {
-    int warps, ipf, nseg, ips, ks, block_bytes, grid;
+    int warps, cpt, lanes, ipf, nseg, ips, bundle, ks, block_bytes, grid;
     StreamLayout L;
     bool ok, bad_tuning;
 };
@@ -129,23 +130,44 @@ StreamShape stream_shape(int64_t F, int64_t N, int n_off, int64_t top_k, const p
         ss.bad_tuning = true;
         return ss;
     }
-    ss.ipf = (int)((N + 31) / 32);
+    // rows per thread: one.  (Two rows per thread at n_off 36 -- 72 offset registers either way, items twice as large -- is
+    // compiled for experiments, PHNMS_STREAM_CPT=2: measured slower, 0.64 vs 0.73 of the roofline at N = 1000, top_k = 4.)
+    ss.cpt = 1;
+    if (g_env.stream_cpt == 2 && n_off == 36) ss.cpt = 2;
+    ss.lanes = t.lanes_per_pass ? t.lanes_per_pass : g_env.lanes_per_pass;
+    if (ss.lanes == 0) ss.lanes = (top_k < 0 || top_k >= 2) ? 2 : 1;
+    if (ss.lanes != 1 && ss.lanes != 2 && ss.lanes != 4) {
+        ss.bad_tuning = true;
+        return ss;
+    }
+    ss.ipf = (int)((N + 32 * ss.cpt - 1) / (32 * ss.cpt));
     if (ss.ipf < 1) ss.ipf = 1;   // (N == 0 is answered before any launch; keep the arithmetic below defined)
+    const int kk = top_k < 0 ? kStreamMaxK : (int)top_k;
+    ss.block_bytes = kBlkHdr + kk * (kHdr + 4 * ((P + 3) & ~3));
     ss.nseg = 1;
-    if (F < sms) ss.nseg = (int)((sms + F - 1) / (F > 0 ? F : 1));
-    if (ss.nseg > ss.ipf) ss.nseg = ss.ipf;
-    if (ss.nseg < 1) ss.nseg = 1;
-    ss.ips = (ss.ipf + ss.nseg - 1) / ss.nseg;
-    ss.nseg = (ss.ipf + ss.ips - 1) / ss.ips;
+    ss.bundle = 1;
+    if (F < sms) {   // fewer frames than SMs: cut a frame into segments so that every SM has work
+        ss.nseg = (int)((sms + F - 1) / (F > 0 ? F : 1));
+        if (ss.nseg > ss.ipf) ss.nseg = ss.ipf;
+        if (ss.nseg < 1) ss.nseg = 1;
+    } else if (ss.ipf < ss.warps) {
+        // small frames: a unit is a bundle of consecutive frames, so that every warp of the CTA has an item in every unit (the
+        // warps then move through the kept-block ring together); bounded by the shared memory the ring may take
+        ss.bundle = (ss.warps + ss.ipf - 1) / ss.ipf;
+        const int max_bundle = (24 * 1024) / (4 * ss.block_bytes);
+        if (ss.bundle > max_bundle) ss.bundle = max_bundle;
+        if ((long long)ss.bundle * sms > F) ss.bundle = (int)(F / sms);   // (never fewer units than SMs)
+        if (ss.bundle < 1) ss.bundle = 1;
+    }
+    ss.ips = ss.bundle > 1 ? ss.bundle * ss.ipf : (ss.ipf + ss.nseg - 1) / ss.nseg;
+    if (ss.bundle == 1) ss.nseg = (ss.ipf + ss.ips - 1) / ss.ips;
     ss.ks = (ss.warps + ss.ips - 1) / ss.ips + 3;
     if (ss.ks < 4) ss.ks = 4;
     if (ss.ks > kStreamMaxRing) ss.ks = kStreamMaxRing;
-    const int kk = top_k < 0 ? kStreamMaxK : (int)top_k;
-    ss.block_bytes = kBlkHdr + kk * (kHdr + 4 * ((P + 3) & ~3));
-    ss.L = stream_layout(ss.warps, P, ss.block_bytes, ss.ks);
-    while (ss.L.total > smem_max && ss.ks > 4) ss.L = stream_layout(ss.warps, P, ss.block_bytes, --ss.ks);
-    while (ss.L.total > smem_max && ss.warps > 1) ss.L = stream_layout(--ss.warps, P, ss.block_bytes, ss.ks);
-    const long long units = (long long)F * ss.nseg;
+    ss.L = stream_layout(ss.warps, P, ss.block_bytes, ss.ks, ss.cpt, ss.bundle);
+    while (ss.L.total > smem_max && ss.ks > 4) ss.L = stream_layout(ss.warps, P, ss.block_bytes, --ss.ks, ss.cpt, ss.bundle);
+    while (ss.L.total > smem_max && ss.warps > 1) ss.L = stream_layout(--ss.warps, P, ss.block_bytes, ss.ks, ss.cpt, ss.bundle);
+    const long long units = ss.bundle > 1 ? (F + ss.bundle - 1) / ss.bundle : (long long)F * ss.nseg;
     long long grid = units < sms ? units : sms;
     if (t.max_clusters > 0 && grid > t.max_clusters) grid = t.max_clusters;
     if (grid < 1) grid = 1;
@@ -610,26 +632,28 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
         q.blocks = blocks; q.block_bytes = ss.block_bytes;
         q.flags = flags; q.ctrs = ctrs; q.list = list;
         q.F = F; q.N = (int)N; q.top_k = (int)top_k; q.sort_model = sort_model; q.thr = thresh;
-        q.ipf = ss.ipf; q.nseg = ss.nseg; q.ips = ss.ips; q.ks = ss.ks;
+        q.ipf = ss.ipf; q.nseg = ss.nseg; q.ips = ss.ips; q.ks = ss.ks; q.bundle = ss.bundle;
         q.off_ring = ss.L.off_ring; q.off_slots = ss.L.off_slots; q.slot_bytes = ss.L.slot_bytes; q.off_bit = ss.L.off_bit;
-        int lanes = t.lanes_per_pass ? t.lanes_per_pass : g_env.lanes_per_pass;
-        if (lanes == 0) lanes = top_k >= 4 ? 4 : (top_k >= 2 ? 2 : 1);
-        if (lanes != 1 && lanes != 2 && lanes != 4) return PHNMS_ERR_TUNING;
+        const int lanes = ss.lanes;
         int rc = 0;
-#define PHNMS_LAUNCH_STREAM(NO, NK)                                                                                   \
+#define PHNMS_LAUNCH_STREAM(NO, NK, CP)                                                                               \
     do {                                                                                                              \
-        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_stream_kernel<NO, NK>), dev.smem_optin);            \
+        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_stream_kernel<NO, NK, CP>), dev.smem_optin);        \
         if (rc) return fail_at("stream smem attribute", rc);                                                          \
-        phnms_stream_kernel<NO, NK><<<(unsigned)ss.grid, ss.warps * 32, (size_t)ss.L.total, stream>>>(q);             \
+        phnms_stream_kernel<NO, NK, CP><<<(unsigned)ss.grid, ss.warps * 32, (size_t)ss.L.total, stream>>>(q);         \
     } while (0)
         if (n_off == 72) {
-            if (lanes == 4) PHNMS_LAUNCH_STREAM(72, 4);
-            else if (lanes == 2) PHNMS_LAUNCH_STREAM(72, 2);
-            else PHNMS_LAUNCH_STREAM(72, 1);
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(72, 4, 1);
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(72, 2, 1);
+            else PHNMS_LAUNCH_STREAM(72, 1, 1);
+        } else if (ss.cpt == 2) {
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(36, 4, 2);
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(36, 2, 2);
+            else PHNMS_LAUNCH_STREAM(36, 1, 2);
         } else {
-            if (lanes == 4) PHNMS_LAUNCH_STREAM(36, 4);
-            else if (lanes == 2) PHNMS_LAUNCH_STREAM(36, 2);
-            else PHNMS_LAUNCH_STREAM(36, 1);
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(36, 4, 1);
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(36, 2, 1);
+            else PHNMS_LAUNCH_STREAM(36, 1, 1);
         }
 #undef PHNMS_LAUNCH_STREAM
         cudaError_t e = cudaGetLastError();

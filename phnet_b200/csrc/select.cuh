@@ -23,6 +23,12 @@
 
 namespace phnms {
 
+#ifndef PHNMS_SELECT_CHUNK
+#define PHNMS_SELECT_CHUNK 16
+#endif
+#ifndef PHNMS_SELECT_CTAS
+#define PHNMS_SELECT_CTAS 6
+#endif
 constexpr int kSelWarps = 4;
 constexpr int kSelBatch = 8;       // proposals drawn per batch (one per lane 0..7)
 constexpr int kSelCapDefault = 64; // draws per frame before it is left open
@@ -53,7 +59,26 @@ inline size_t select_smem_bytes(int N, int n_off, int top_k, int warps) {
     return (size_t)warps * select_warp_words(N, n_off, top_k) * 4;
 }
 
-__global__ void __launch_bounds__(kSelWarps * 32) phnms_select_kernel(const SelectParams sp) {
+// key_desc (common.cuh) without the NaN-first case, in four integer instructions: ascending-u32 == descending score, -0.0 folded
+// onto +0.0.  Positive floats: the low 31 bits inverted (larger score -> smaller key, top bit 0); negative floats: the bit
+// pattern itself (top bit 1, larger magnitude -> larger key).  Same values as key_desc(s, false).
+__device__ __forceinline__ uint32_t key_desc_fast(float s) {
+    uint32_t u = __float_as_uint(s);
+    if (u == 0x80000000u) u = 0u;
+    return u ^ ((uint32_t)((int32_t)~u >> 31) & 0x7fffffffu);
+}
+
+// the 28 pairs (a < b) of a batch of 8, packed 4 bits per pair: lane -> (a, b)
+__device__ __forceinline__ void batch_pair(int lane, int &a, int &b) {
+    // (0,1)(0,2)(0,3)(0,4)(0,5)(0,6)(0,7)(1,2)(1,3)(1,4)(1,5)(1,6)(1,7)(2,3)(2,4)(2,5) | (2,6)(2,7)(3,4)(3,5)(3,6)(3,7)(4,5)(4,6)(4,7)(5,6)(5,7)(6,7)
+    const unsigned long long A0 = 0x2221111110000000ull, B0 = 0x5437654327654321ull;
+    const unsigned long long A1 = 0x0000655444333322ull, B1 = 0x0000776765765476ull;
+    const int sh = 4 * (lane & 15);
+    a = (int)(((lane < 16 ? A0 : A1) >> sh) & 15ull);
+    b = (int)(((lane < 16 ? B0 : B1) >> sh) & 15ull);
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_select_kernel(const SelectParams sp) {
     extern __shared__ __align__(16) unsigned char smem_sel[];
     __shared__ float bit_key[kSelWarps][32];
     __shared__ int bit_val[kSelWarps][32];
@@ -106,37 +131,43 @@ __global__ void __launch_bounds__(kSelWarps * 32) phnms_select_kernel(const Sele
         }
         if (lane < n) sorted = ((u64)(uint32_t)lane << 32) | (uint32_t)bv[lane];  // the sorted position is the rank key
     } else if (n > 0) {
+        // Rank keys of the whole frame -> shared memory (lane l owns proposals l, l + 32, ...), the lane's smallest key in a
+        // register.  Chunks of 8 keys per lane; a chunk that lies entirely inside the frame needs no bounds predicates, and
+        // within a lane a strict `<` keeps the earliest (smallest-index) proposal among equal keys.
         const bool nan_first = sp.sort_model == 1;
-        if (G <= 32) {   // up to 1024 proposals: all score loads are issued before the first one is consumed
-            float sv[32];
+        uint32_t *kbl = kb + lane * pitch;
+        const int cnt = lane < n ? ((n - lane + 31) >> 5) : 0;   // keys this lane owns
+        uint32_t bestk = 0xffffffffu;
+        int bestq = 0;
+        constexpr int KC = PHNMS_SELECT_CHUNK;   // keys per lane whose loads are in flight together
+        for (int q0 = 0; q0 < G; q0 += KC) {
+            if (!nan_first && 32 * (q0 + KC) <= n) {
+                float sv[KC];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const int i = lane + 32 * q;
-                sv[q] = (q < G && i < n) ? sc[i] : 0.0f;
-            }
+                for (int u = 0; u < KC; ++u) sv[u] = sc[lane + 32 * (q0 + u)];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const int i = lane + 32 * q;
-                if (q < G) {
+                for (int u = 0; u < KC; ++u) {
+                    const uint32_t k = key_desc_fast(sv[u]);
+                    if (k < bestk) { bestk = k; bestq = q0 + u; }
+                    kbl[q0 + u] = k;
+                }
+            } else {
+                float sv[KC];
+#pragma unroll
+                for (int u = 0; u < KC; ++u) sv[u] = (q0 + u < cnt) ? sc[lane + 32 * (q0 + u)] : 0.0f;
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    const int q = q0 + u;
                     uint32_t k = 0xffffffffu;
-                    if (i < n) {
-                        k = key_desc(sv[q], nan_first);
-                        gmin = min(gmin, ((u64)k << 32) | (uint32_t)i);
+                    if (q < cnt) {
+                        k = key_desc(sv[u], nan_first);
+                        if (k < bestk) { bestk = k; bestq = q; }   // (all-ones keys: bestq stays 0, the earliest)
                     }
-                    kb[lane * pitch + q] = k;
+                    if (q < G) kbl[q] = k;
                 }
-            }
-        } else {
-            for (int q = 0; q < G; ++q) {
-                const int i = lane + 32 * q;
-                uint32_t k = 0xffffffffu;
-                if (i < n) {
-                    k = key_desc(sc[i], nan_first);
-                    gmin = min(gmin, ((u64)k << 32) | (uint32_t)i);
-                }
-                kb[lane * pitch + q] = k;
             }
         }
+        if (cnt > 0) gmin = ((u64)bestk << 32) | (uint32_t)(lane + 32 * bestq);
         __syncwarp();
     }
 
@@ -216,12 +247,9 @@ __global__ void __launch_bounds__(kSelWarps * 32) phnms_select_kernel(const Sele
         // ---- survivors against each other (strict upper triangle in rank order, :85-87), then the scan over the batch ------
         const int s = __popc(surv), need = top_k - nk;
         if (s >= 2 && need >= 2) {
-            const int np = s * (s - 1) / 2;   // <= 28
-            if (lane < np) {
-                int ia = 0, rem = lane;
-                while (rem >= s - 1 - ia) { rem -= s - 1 - ia; ++ia; }
-                const int ib = ia + 1 + rem;
-                const int a = (int)__fns(surv, 0, ia + 1), b = (int)__fns(surv, 0, ib + 1);
+            int a, b;
+            batch_pair(lane, a, b);
+            if (lane < 28 && ((surv >> a) & (surv >> b) & 1u)) {
                 if (pair_hit_scalar(brow + a * bp, brow + b * bp, bse[2 * a], bse[2 * a + 1], bse[2 * b], bse[2 * b + 1], sp.thr))
                     atomicOr(&adj[a], 1u << b);
             }

@@ -7,7 +7,8 @@
 //
 //     parent[j] = 1 + max{ k : kept lane k is ranked before j and devIoU(kept_k, j) }   (or k + 1 if j IS kept lane k)
 //
-// No cluster, no per-frame barrier, no exchange: the unit of work is a 32-row ITEM owned by one warp.
+// No cluster, no per-frame barrier, no exchange: the unit of work is an ITEM of 32 x CPT rows owned by one warp (CPT rows per
+// thread: 1 at 72 offsets, 2 at 36 -- 72 offset registers per thread either way).
 //   * each warp owns a private staging slot in shared memory and feeds it itself: one TMA 1-D bulk copy (UBLKCP) of the
 //     item's 16-byte aligned body + 4-byte cp.async (LDGSTS) for <= 3 unaligned words at either end and for the 32 scores,
 //     all completing on the warp's own mbarrier (cp.async.mbarrier.arrive.noinc);
@@ -45,9 +46,10 @@ struct StreamParams {
     long long F;
     int N, top_k, sort_model;
     float thr;
-    int ipf;    // 32-row items per frame: ceil(N / 32)
+    int ipf;    // items per frame: ceil(N / rows per item), rows per item = 32 x rows per thread
     int nseg;   // a frame is cut into nseg units of ips item slots (nseg > 1 only when there are fewer frames than CTAs)
     int ips;
+    int bundle; // ... or a unit is a bundle of consecutive frames (small frames: so that every warp has an item in every unit)
     int ks;     // kept-block ring slots
     int off_ring, off_slots, slot_bytes, off_bit;
 };
@@ -56,15 +58,15 @@ struct StreamLayout {
     int off_ring, off_slots, slot_bytes, off_bit, total;
 };
 
-// shared memory: [0,128) row mbarriers (one per warp) | [128,384) kfull | [384,640) kempty | [640] request ticket
-__host__ __device__ inline StreamLayout stream_layout(int warps, int P, int block_bytes, int ks) {
+// shared memory: [0,128) row mbarriers (one per warp) | [128,384) kfull | [384,640) kempty | [640] next ticket | [644] tickets issued
+__host__ __device__ inline StreamLayout stream_layout(int warps, int P, int block_bytes, int ks, int cpt, int bundle) {
     StreamLayout L;
     int o = 768;
     L.off_ring = o;
-    o += ks * block_bytes;
+    o += ks * block_bytes * (bundle > 1 ? bundle : 1);
     o = (o + 127) & ~127;
     L.off_slots = o;
-    L.slot_bytes = 128 + ((16 + 32 * P * 4 + 16 + 127) & ~127);   // 32 scores | rows (16 B lead for the alignment shift)
+    L.slot_bytes = 128 * cpt + ((16 + 32 * cpt * P * 4 + 16 + 127) & ~127);   // scores | rows (16 B lead for the alignment shift)
     o += warps * L.slot_bytes;
     L.off_bit = o;
     o += warps * 384;
@@ -91,18 +93,19 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 
 // devIoU (nms_kernel.cu:26-48) of NK kept lanes -- consecutive slots starting at shared address s0 -- against this thread's
-// proposal, in ONE pass over its registers: NK independent fp32 chains, each the reference's ascending sequential sum
-// (:38-44).  Row word i of kept lane k enters the sum iff bit i of (ma_k & mb) is set: the pair's range
+// CPT proposals, in ONE pass over its registers: NK x CPT independent fp32 chains, each the reference's ascending sequential
+// sum (:38-44).  Row word i of kept lane k enters a proposal's sum iff bit i of (ma_k & mb) is set: the pair's range
 // [max(sa, sb), min(ea, eb)] is the intersection of the two lanes' own ranges -- which needs max(sa, sb) >= 0 (below, header
 // words or the wrapped unsigned-char counter come into play, :38): if any active pair of the warp has a negative start the
 // function returns false and the caller takes the exact one-lane evaluator (freg_eval).  All addresses are one register +
-// immediates; what stays live across the pass is dist / limit per lane and one word of flags.
-template <int NOFF, int NK>
-__device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, bool live, u64 myK, int st, int en,
-                                            const uint32_t (&mb)[(5 + NOFF + 31) / 32], const float (&x)[NOFF], float thr,
-                                            uint32_t &par, int k0) {
+// immediates; what stays live across the pass is dist / limit per chain and one word of flags.
+template <int NOFF, int NK, int CPT>
+__device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, const bool (&live)[CPT], const u64 (&myK)[CPT],
+                                            const int (&st)[CPT], const int (&en)[CPT],
+                                            const uint32_t (&mb)[CPT][(5 + NOFF + 31) / 32], const float (&x)[CPT][NOFF],
+                                            float thr, uint32_t (&par)[CPT], int k0) {
     constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4;
-    float lim[NK], dist[NK];
+    float lim[NK][CPT], dist[NK][CPT];
     uint32_t self = 0u;
     bool rare = false;
 #pragma unroll
@@ -110,20 +113,27 @@ __device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, bool live, u64
         const uint4 wh = lds_u4(s0 + k * SLOT);
         const u64 wk = k < cnt ? (((u64)wh.x << 32) | wh.y) : kNone64;   // a padding lane activates nobody
         const int sa = (int)wh.z, ea = (int)wh.w;
-        const int start = max(sa, st), end = min(ea, en);                 // :31,:34 (both ends clamped to NOFF-1)
-        const bool act = live && (myK > wk) && (end >= start);            // ranked after the kept lane; :36
-        rare |= act && (start < 0);
-        const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
-        lim[k] = act ? __fmul_rn(thr, (float)len) : -__int_as_float(0x7f800000);   // :46; -inf: never a hit
-        if (myK == wk) self |= 1u << k;
-        dist[k] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int start = max(sa, st[c]), end = min(ea, en[c]);           // :31,:34 (both ends clamped to NOFF-1)
+            const bool act = live[c] && (myK[c] > wk) && (end >= start);      // ranked after the kept lane; :36
+            rare |= act && (start < 0);
+            const int len = (int)((uint32_t)end - (uint32_t)start + 1u);
+            lim[k][c] = act ? __fmul_rn(thr, (float)len) : -__int_as_float(0x7f800000);   // :46; -inf: never a hit
+            if (myK[c] == wk) self |= 1u << (k * CPT + c);
+            dist[k][c] = 0.0f;
+        }
     }
     if (__any_sync(0xffffffffu, rare)) return false;
 #pragma unroll
     for (int w = 0; w < MW; ++w) {
-        uint32_t m[NK];   // pair masks of this 32-word span
+        uint32_t m[NK][CPT];   // pair masks of this 32-word span
 #pragma unroll
-        for (int k = 0; k < NK; ++k) m[k] = lds_u32(s0 + k * SLOT + 16 + 4 * w) & mb[w];
+        for (int k = 0; k < NK; ++k) {
+            const uint32_t ma = lds_u32(s0 + k * SLOT + 16 + 4 * w);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) m[k][c] = ma & mb[c][w];
+        }
 #pragma unroll
         for (int g = 8 * w; g < 8 * w + 8; ++g) {
             if (g >= 1 && g < P4 / 4) {
@@ -135,15 +145,18 @@ __device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, bool live, u64
                     for (int u = 0; u < 4; u += 2) {
                         const int i = 4 * g + u;
                         const bool v0 = i >= 5 && i < P, v1 = i + 1 >= 5 && i + 1 < P;
-                        float t0 = 0.0f, t1 = 0.0f;
-                        if (v0 && v1) {
-                            fsub2(a4[u], a4[u + 1], x[v0 ? i - 5 : 0], x[v1 ? i - 4 : 0], t0, t1);
-                        } else {
-                            if (v0) t0 = __fsub_rn(a4[u], x[v0 ? i - 5 : 0]);
-                            if (v1) t1 = __fsub_rn(a4[u + 1], x[v1 ? i - 4 : 0]);
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            float t0 = 0.0f, t1 = 0.0f;
+                            if (v0 && v1) {
+                                fsub2(a4[u], a4[u + 1], x[c][v0 ? i - 5 : 0], x[c][v1 ? i - 4 : 0], t0, t1);
+                            } else {
+                                if (v0) t0 = __fsub_rn(a4[u], x[c][v0 ? i - 5 : 0]);
+                                if (v1) t1 = __fsub_rn(a4[u + 1], x[c][v1 ? i - 4 : 0]);
+                            }
+                            if (v0 && (m[k][c] & (1u << (i & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t0));
+                            if (v1 && (m[k][c] & (1u << ((i + 1) & 31)))) dist[k][c] = __fadd_rn(dist[k][c], fabsf(t1));
                         }
-                        if (v0 && (m[k] & (1u << (i & 31)))) dist[k] = __fadd_rn(dist[k], fabsf(t0));
-                        if (v1 && (m[k] & (1u << ((i + 1) & 31)))) dist[k] = __fadd_rn(dist[k], fabsf(t1));
                     }
                 }
             }
@@ -151,13 +164,15 @@ __device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, bool live, u64
     }
 #pragma unroll
     for (int k = 0; k < NK; ++k)      // in keep order: the last kept lane that covers a proposal wins (:127)
-        if (k < cnt && ((dist[k] < lim[k]) || ((self >> k) & 1u))) par = (uint32_t)(k0 + k + 1);   // :46,:127,:129
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+            if (k < cnt && ((dist[k][c] < lim[k][c]) || ((self >> (k * CPT + c)) & 1u))) par[c] = (uint32_t)(k0 + k + 1);   // :46,:127,:129
     return true;
 }
 
-template <int NOFF, int NKP>
+template <int NOFF, int NKP, int CPT>
 __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(const StreamParams sp) {
-    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4;
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4, RPI = 32 * CPT;   // rows per item
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t bar_rows = smem_u32(smem) + 8u * warp;
@@ -166,210 +181,289 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
     unsigned char *ring = smem + sp.off_ring;
     unsigned char *myslot = smem + sp.off_slots + (size_t)warp * sp.slot_bytes;
     float *sc_buf = reinterpret_cast<float *>(myslot);
-    unsigned char *rows_base = myslot + 128;
-    const int ks = sp.ks, ips = sp.ips, nseg = sp.nseg;
+    unsigned char *rows_base = myslot + 128 * CPT;
+    const uint32_t ks = (uint32_t)sp.ks, ips = (uint32_t)sp.ips;
+    const int nseg = sp.nseg;
 
     if (tid == 0) {
         for (int w = 0; w < nwarps; ++w) mbar_init(smem_u32(smem) + 8u * w, 33);   // 1 expect_tx arrive + 32 cp.async arrives
-        for (int s = 0; s < ks; ++s) {
+        for (uint32_t s = 0; s < ks; ++s) {
             mbar_init(kfull0 + 8u * s, 1);
-            mbar_init(kempty0 + 8u * s, (uint32_t)ips);   // one arrive per item slot of the unit
+            mbar_init(kempty0 + 8u * s, ips);   // one arrive per item slot of the unit
         }
-        *next_req = 0u;
+        next_req[0] = 0u;
+        next_req[1] = 0u;   // `issued`
         fence_mbar_init();
     }
     __syncthreads();
 
-    // units of this CTA: u = b, b + G, ...; unit u = (frame u / nseg, segment u % nseg); item slots m = us * ips + ci
-    const long long U = sp.F * nseg;
+    // units of this CTA: u = b, b + G, ...; unit u = (frame u / nseg, segment u % nseg); the unit's item slots ci = 0 .. ips-1
+    // go round the warps: warp w takes the CTA's item slots w, w + nwarps, ... (tracked incrementally as (us, ci): no division
+    // on the per-item path unless a unit has fewer item slots than the CTA has warps)
+    const long long U = sp.bundle > 1 ? (sp.F + sp.bundle - 1) / sp.bundle : sp.F * nseg;
     const uint32_t b = blockIdx.x, G = gridDim.x;
     const uint32_t nu = b < U ? (uint32_t)((U - b + G - 1) / G) : 0u;
-    const uint32_t M = nu * (uint32_t)ips;   // (the host keeps this below 2^31)
-    const int look = ks - 2;
-    if (M == 0u) return;
+    const int look = (int)ks - 2;
+    const uint32_t ring_slot = (uint32_t)sp.block_bytes * (uint32_t)(sp.bundle > 1 ? sp.bundle : 1);
+    if (nu == 0u) return;
 
-    struct Item { long long f; int r0, nrows, us; bool valid; };
-    auto decode = [&](uint32_t m) {
+    struct Item { long long f; int r0, nrows, fb; bool valid; };
+    const int bundle = sp.bundle;
+    auto decode = [&](uint32_t us, uint32_t ci) {
         Item it;
-        const uint32_t us = m / (uint32_t)ips;
-        const int ci = (int)(m - us * (uint32_t)ips);
         const long long u = (long long)b + (long long)us * G;
-        it.f = nseg == 1 ? u : u / nseg;
-        const int sg = (int)(u - it.f * nseg);
-        const int c = sg * ips + ci;
-        it.valid = c < sp.ipf;
-        it.r0 = c * 32;
-        it.us = (int)us;
+        int c;
+        it.fb = 0;
+        if (bundle > 1) {          // unit = frames u * bundle .. ; item slot ci = (frame within the bundle, item of the frame)
+            it.fb = (int)(ci / (uint32_t)sp.ipf);
+            c = (int)ci - it.fb * sp.ipf;
+            it.f = u * bundle + it.fb;
+            it.valid = it.f < sp.F;
+            if (!it.valid) it.f = sp.F - 1;
+        } else {
+            it.f = nseg == 1 ? u : u / nseg;
+            const int sg = (int)(u - it.f * nseg);
+            c = sg * (int)ips + (int)ci;
+            it.valid = c < sp.ipf;
+        }
+        it.r0 = c * RPI;
         int nv = sp.N;
         if (sp.n_valid) nv = max(0, min(sp.n_valid[it.f], sp.N));
-        it.nrows = it.valid ? max(0, min(nv - it.r0, 32)) : 0;
+        it.nrows = it.valid ? max(0, min(nv - it.r0, RPI)) : 0;
         return it;
+    };
+    auto advance = [&](uint32_t &us, uint32_t &ci, uint32_t &kslot, uint32_t &kpar) {
+        ci += (uint32_t)nwarps;
+        if (ci >= ips) {
+            uint32_t d = 1u;
+            if (ips >= (uint32_t)nwarps) {
+                ci -= ips;
+            } else {
+                d = ci / ips;
+                ci -= d * ips;
+            }
+            us += d;
+            kslot += d;
+            while (kslot >= ks) {
+                kslot -= ks;
+                kpar ^= 1u;
+            }
+        }
     };
     // the item's rows -> this warp's slot.  Row data keeps its global address modulo 16 (rows are only 4-byte aligned:
     // 308 / 164 bytes), so the aligned body is one bulk copy and at most 3 words at either end are copied singly.
     auto issue = [&](const Item &it) {
         if (it.nrows <= 0) return;
         const float *src = sp.props + ((size_t)it.f * sp.N + it.r0) * P;
-        const uintptr_t a0 = (uintptr_t)src, bytes = (uintptr_t)it.nrows * P * 4;
-        const uintptr_t b0 = (a0 + 15) & ~(uintptr_t)15, e0 = (a0 + bytes) & ~(uintptr_t)15;
-        unsigned char *D = rows_base + (a0 & 15);
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar_rows, (uint32_t)(e0 - b0));
-            bulk_g2s(smem_u32(D + (b0 - a0)), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
+        const float *ssrc = sp.scores + (size_t)it.f * sp.N + it.r0;
+        const uintptr_t a0 = (uintptr_t)src;
+        const uint32_t bytes = (uint32_t)it.nrows * (P * 4);
+        if (((a0 | bytes) & 15u) == 0u) {   // the usual case: N a multiple of 4 and an aligned tensor
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_rows, bytes);
+                bulk_g2s(smem_u32(rows_base), src, bytes, bar_rows);
+            }
+        } else {
+            const uintptr_t b0 = (a0 + 15) & ~(uintptr_t)15, e0 = (a0 + bytes) & ~(uintptr_t)15;
+            unsigned char *D = rows_base + (a0 & 15);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_rows, (uint32_t)(e0 - b0));
+                bulk_g2s(smem_u32(D + (b0 - a0)), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
+            }
+            const int hw = (int)((b0 - a0) >> 2), tw = (int)((a0 + bytes - e0) >> 2), t0 = (int)((e0 - a0) >> 2);
+            if (lane >= 1 && lane - 1 < hw) cp_async_4(smem_u32(D + 4 * (lane - 1)), src + (lane - 1));
+            if (lane >= 4 && lane - 4 < tw) cp_async_4(smem_u32(D + 4 * (t0 + lane - 4)), src + t0 + (lane - 4));
         }
-        const int hw = (int)((b0 - a0) >> 2), tw = (int)((a0 + bytes - e0) >> 2), t0 = (int)((e0 - a0) >> 2);
-        if (lane >= 1 && lane - 1 < hw) cp_async_4(smem_u32(D + 4 * (lane - 1)), src + (lane - 1));
-        if (lane >= 4 && lane - 4 < tw) cp_async_4(smem_u32(D + 4 * (t0 + lane - 4)), src + t0 + (lane - 4));
-        if (lane < it.nrows) cp_async_4(smem_u32(sc_buf + lane), sp.scores + (size_t)it.f * sp.N + it.r0 + lane);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+            if (c * 32 + lane < it.nrows) cp_async_4(smem_u32(sc_buf + c * 32 + lane), ssrc + c * 32 + lane);
         cp_async_mbar_arrive_noinc(bar_rows);
     };
-    // kept blocks: requested up to `look` units ahead by whichever warp gets there first (lane 0 only)
+    // kept blocks: requested up to `look` units ahead by whichever warp gets there first (lane 0 only).  Requests go out in
+    // TICKET ORDER (`issued` counts them): mbarrier waits only tell even from odd phases, so nobody may get two phases ahead
+    // of a barrier -- when a frame has fewer item slots than the CTA has warps, different warps work on different units and
+    // drift apart; without the ordering a warp far ahead could pass the wait for "the previous user of this ring slot is
+    // done" on the strength of the user before that.  A ticket waits for units older than every unit its claimer (or any warp
+    // spinning on `issued`) is working on, so the oldest unfinished unit can always finish: no cycle.
+    volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(smem + 644);
+    auto spin_until_issued = [&](uint32_t t) {   // returns once ticket t has been requested
+        if (*issued > t) return;
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*issued <= t) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > kMbarTimeoutNs) __trap();
+        }
+    };
     auto ensure_requested = [&](long long upto) {
         for (;;) {
             const uint32_t t = *reinterpret_cast<volatile uint32_t *>(next_req);
             if ((long long)t > upto || t >= nu) break;
             if (atomicCAS(next_req, t, t + 1u) != t) continue;
-            const uint32_t slot = t % (uint32_t)ks, use = t / (uint32_t)ks;
+            if (t > 0u) spin_until_issued(t - 1u);
+            const uint32_t slot = t % ks, use = t / ks;
             if (use > 0u) mbar_wait(kempty0 + 8u * slot, (use - 1u) & 1u);   // every item slot of the previous user is done
             const long long uq = (long long)b + (long long)t * G;
-            const long long fq = nseg == 1 ? uq : uq / nseg;
-            mbar_arrive_expect_tx(kfull0 + 8u * slot, (uint32_t)sp.block_bytes);
-            bulk_g2s(smem_u32(ring + (size_t)slot * sp.block_bytes), sp.blocks + (size_t)fq * sp.block_bytes,
-                     (uint32_t)sp.block_bytes, kfull0 + 8u * slot);
+            const long long fq = bundle > 1 ? uq * bundle : (nseg == 1 ? uq : uq / nseg);
+            const long long nb = bundle > 1 ? min((long long)bundle, sp.F - fq) : 1;   // blocks of consecutive frames are contiguous
+            const uint32_t nbytes = (uint32_t)nb * (uint32_t)sp.block_bytes;
+            mbar_arrive_expect_tx(kfull0 + 8u * slot, nbytes);
+            bulk_g2s(smem_u32(ring + (size_t)slot * ring_slot), sp.blocks + (size_t)fq * sp.block_bytes, nbytes, kfull0 + 8u * slot);
+            __threadfence_block();
+            *issued = t + 1u;
         }
     };
 
     uint32_t rphase = 0u;
-    uint32_t m = (uint32_t)warp;
-    if (m < M) {
-        const Item first = decode(m);
-        issue(first);
-        if (lane == 0) ensure_requested((long long)first.us + look);
+    // this warp's first item slot: (us, ci) with us * ips + ci == warp
+    uint32_t us = (uint32_t)warp / ips, ci = (uint32_t)warp - us * ips;
+    uint32_t kslot = us % ks, kpar = (us / ks) & 1u;
+    if (us < nu) {
+        issue(decode(us, ci));
+        if (lane == 0) ensure_requested((long long)us + look);
     }
 
-    for (; m < M; m += (uint32_t)nwarps) {
-        float x[NOFF];
-        int st, en, i_out, nrows;
-        float score = 0.0f;
+    while (us < nu) {
+        float x[CPT][NOFF];
+        int st[CPT], en[CPT], nrows;
+        float score[CPT];
         long long f;
-        uint32_t kslot, kpar;
+        int r0, fb;
         bool valid;
+        const uint32_t my_kslot = kslot, my_kpar = kpar, us_item = us;
         {
-            const Item cur = decode(m);
+            const Item cur = decode(us, ci);
             f = cur.f;
             nrows = cur.nrows;
             valid = cur.valid;
-            i_out = cur.r0 + lane;
-            kslot = (uint32_t)cur.us % (uint32_t)ks;
-            kpar = ((uint32_t)cur.us / (uint32_t)ks) & 1u;
+            r0 = cur.r0;
+            fb = cur.fb;
             if (nrows > 0) {
                 mbar_wait(bar_rows, rphase);
                 rphase ^= 1u;
-                const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)f * sp.N + cur.r0) * P);
-                const float *row = reinterpret_cast<const float *>(rows_base + (a0 & 15)) + (size_t)(lane < nrows ? lane : 0) * P;
+                const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)f * sp.N + r0) * P);
+                const float *rows = reinterpret_cast<const float *>(rows_base + (a0 & 15));
 #pragma unroll
-                for (int i = 0; i < NOFF; ++i) x[i] = row[5 + i];
-                st = lane_start(row[2], NOFF);       // nms_kernel.cu:29-30
-                en = lane_end(row[4], st, NOFF);     // :32-34
-                score = sc_buf[lane < nrows ? lane : 0];
+                for (int c = 0; c < CPT; ++c) {
+                    const int rr = c * 32 + lane < nrows ? c * 32 + lane : 0;
+                    const float *row = rows + (size_t)rr * P;
+#pragma unroll
+                    for (int i = 0; i < NOFF; ++i) x[c][i] = row[5 + i];
+                    st[c] = lane_start(row[2], NOFF);          // nms_kernel.cu:29-30
+                    en[c] = lane_end(row[4], st[c], NOFF);     // :32-34
+                    score[c] = sc_buf[rr];
+                }
             } else {
 #pragma unroll
-                for (int i = 0; i < NOFF; ++i) x[i] = 0.0f;
-                st = 0;
-                en = -1;
+                for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+                    for (int i = 0; i < NOFF; ++i) x[c][i] = 0.0f;
+                    st[c] = 0;
+                    en[c] = -1;
+                    score[c] = 0.0f;
+                }
             }
-            __syncwarp();   // every lane has read its row: the slot is free for the next item
-            if (m + (uint32_t)nwarps < M) issue(decode(m + (uint32_t)nwarps));
-            if (lane == 0) ensure_requested((long long)cur.us + look);
+            __syncwarp();   // every lane has read its rows: the slot is free for the next item
+            const uint32_t us_cur = us;
+            advance(us, ci, kslot, kpar);
+            if (us < nu) issue(decode(us, ci));
+            if (lane == 0) ensure_requested((long long)us_cur + look);
             __syncwarp();
         }
 
         // ---- the frame's kept lanes (block written by the select kernel: {nk, open, n} + slots) -------------------------------
-        mbar_wait(kfull0 + 8u * kslot, kpar);
-        const uint32_t blk_s = smem_u32(ring) + kslot * (uint32_t)sp.block_bytes;
+        spin_until_issued(us_item);   // (the request of this unit's block has gone out: the parity below names the right phase)
+        mbar_wait(kfull0 + 8u * my_kslot, my_kpar);
+        const uint32_t blk_s = smem_u32(ring) + my_kslot * ring_slot + (uint32_t)fb * (uint32_t)sp.block_bytes;
         const int nk = min((int)lds_u32(blk_s), sp.top_k);
         const bool open = lds_u32(blk_s + 4) != 0u;
         const int nvf = (int)lds_u32(blk_s + 8);   // proposals in the frame
 
-        const bool real = lane < nrows;
-        uint32_t key = key_desc(real ? score : 0.0f, sp.sort_model == 1);
+        bool real[CPT];
+        uint32_t key[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            real[c] = c * 32 + lane < nrows;
+            key[c] = key_desc(real[c] ? score[c] : 0.0f, sp.sort_model == 1);
+        }
         // (torch sort model) a frame of <= 32 proposals is ordered by ATen's unstable bitonic network -- the select kernel's
-        // rank keys are then the sorted positions, and so must these be; such a frame is exactly one item (rows 0 .. n-1)
+        // rank keys are then the sorted positions, and so must these be; such a frame is exactly rows 0 .. n-1 of one item
         if (sp.sort_model == 0 && valid && nvf <= 32 && nvf >= 2 && nrows > 0) {
             const int nv = nvf;
-            {
-                float *bit_key = reinterpret_cast<float *>(smem + sp.off_bit + warp * 384);
-                int *bit_val = reinterpret_cast<int *>(bit_key + 32), *bit_ok = bit_val + 32;
-                bit_ok[lane] = lane < nv;
-                bit_key[lane] = lane < nv ? score : 0.0f;
-                bit_val[lane] = lane < nv ? lane : 0;
-                __syncwarp();
-                for (unsigned size = 2; size <= 32; size *= 2) {
-                    const bool flag = (size != 32) && ((lane & (size / 2)) != 0);
-                    for (unsigned stride = size / 2; stride > 0; stride /= 2) {
-                        if (lane < 16) {
-                            const unsigned pa = 2 * lane - (lane & (stride - 1)), pb = pa + stride;
-                            const float ka = bit_key[pa], kb = bit_key[pb];
-                            const int oa = bit_ok[pa], ob = bit_ok[pb];
-                            const bool sw = (gt_nan(ka, kb) && oa) || !ob;
-                            if (sw == flag) {
-                                const int va = bit_val[pa], vb = bit_val[pb];
-                                bit_key[pa] = kb; bit_key[pb] = ka;
-                                bit_val[pa] = vb; bit_val[pb] = va;
-                                bit_ok[pa] = ob;  bit_ok[pb] = oa;
-                            }
+            float *bit_key = reinterpret_cast<float *>(smem + sp.off_bit + warp * 384);
+            int *bit_val = reinterpret_cast<int *>(bit_key + 32), *bit_ok = bit_val + 32;
+            bit_ok[lane] = lane < nv;
+            bit_key[lane] = lane < nv ? score[0] : 0.0f;
+            bit_val[lane] = lane < nv ? lane : 0;
+            __syncwarp();
+            for (unsigned size = 2; size <= 32; size *= 2) {
+                const bool flag = (size != 32) && ((lane & (size / 2)) != 0);
+                for (unsigned stride = size / 2; stride > 0; stride /= 2) {
+                    if (lane < 16) {
+                        const unsigned pa = 2 * lane - (lane & (stride - 1)), pb = pa + stride;
+                        const float ka = bit_key[pa], kb = bit_key[pb];
+                        const int oa = bit_ok[pa], ob = bit_ok[pb];
+                        const bool sw = (gt_nan(ka, kb) && oa) || !ob;
+                        if (sw == flag) {
+                            const int va = bit_val[pa], vb = bit_val[pb];
+                            bit_key[pa] = kb; bit_key[pb] = ka;
+                            bit_val[pa] = vb; bit_val[pb] = va;
+                            bit_ok[pa] = ob;  bit_ok[pb] = oa;
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                 }
-                int mypos = 0;
-                for (int q = 0; q < 32; ++q)
-                    if (bit_val[q] == lane && q < nv) mypos = q;
-                key = (uint32_t)mypos;
-                __syncwarp();
             }
+            int mypos = 0;
+            for (int q = 0; q < 32; ++q)
+                if (bit_val[q] == lane && q < nv) mypos = q;
+            key[0] = (uint32_t)mypos;
+            __syncwarp();
         }
-        const u64 myK = real ? (((u64)key << 32) | (uint32_t)i_out) : kNone64;
-        uint32_t mb[MW], par = 0u;
-        range_mask<MW>(st, en, mb);
+        u64 myK[CPT];
+        uint32_t mb[CPT][MW], par[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            myK[c] = real[c] ? (((u64)key[c] << 32) | (uint32_t)(r0 + c * 32 + lane)) : kNone64;
+            par[c] = 0u;
+            range_mask<MW>(st[c], en[c], mb[c]);
+        }
 
         if (valid) {
             if (nrows > 0) {
                 for (int k0 = 0; k0 < nk; k0 += NKP) {
                     const int cnt = min(NKP, nk - k0);
-                    if (!stream_eval<NOFF, NKP>(blk_s + kBlkHdr + (uint32_t)k0 * SLOT, cnt, real, myK, st, en, mb, x, sp.thr, par, k0)) {
+                    if (!stream_eval<NOFF, NKP, CPT>(blk_s + kBlkHdr + (uint32_t)k0 * SLOT, cnt, real, myK, st, en, mb, x, sp.thr, par, k0)) {
                         // a pair with a negative common start somewhere in the warp: the exact evaluator, one lane at a time
                         FusedParams fp;
                         fp.thr = sp.thr;
-                        auto my_hdr = [&](int) { return sp.props + ((size_t)f * sp.N + (uint32_t)i_out) * P; };
-                        const bool live1[1] = {real};
-                        const u64 myK1[1] = {myK};
-                        const int st1[1] = {st}, en1[1] = {en};
-                        uint32_t mb1[1][MW], par1[1] = {par};
-#pragma unroll
-                        for (int w = 0; w < MW; ++w) mb1[0][w] = mb[w];
+                        auto my_hdr = [&](int c) { return sp.props + ((size_t)f * sp.N + (uint32_t)(r0 + c * 32 + lane)) * P; };
                         for (int k = 0; k < cnt; ++k) {
-                            const unsigned char *const h1[1] = {ring + (size_t)kslot * sp.block_bytes + kBlkHdr + (size_t)(k0 + k) * SLOT};
-                            bool hit[1][1];
-                            freg_eval<NOFF, 1, 1>(fp, f, h1, live1, myK1, st1, en1, mb1, reinterpret_cast<const float (&)[1][NOFF]>(x),
-                                                  my_hdr, par1, hit, k0 + k);
+                            const unsigned char *const h1[1] = {ring + (size_t)my_kslot * ring_slot + (size_t)fb * sp.block_bytes + kBlkHdr + (size_t)(k0 + k) * SLOT};
+                            bool hit[1][CPT];
+                            freg_eval<NOFF, CPT, 1>(fp, f, h1, real, myK, st, en, mb, x, my_hdr, par, hit, k0 + k);
                         }
-                        par = par1[0];
                     }
                 }
             }
             // ---- outputs, written once ------------------------------------------------------------------------------------
-            if (i_out < sp.N) {
-                st_global_cs_u64(sp.parent + (size_t)f * sp.N + i_out, (long long)par);
-                if (i_out >= nk) st_global_cs_u64(sp.keep + (size_t)f * sp.N + i_out, 0ll);   // :139-140
+            bool alive = false;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int i_out = r0 + c * 32 + lane;
+                if (i_out < sp.N) {
+                    st_global_cs_u64(sp.parent + (size_t)f * sp.N + i_out, (long long)par[c]);
+                    if (i_out >= nk) st_global_cs_u64(sp.keep + (size_t)f * sp.N + i_out, 0ll);   // :139-140
+                }
+                alive |= real[c] && par[c] == 0u;
             }
             // an open frame with a proposal nobody covers has more lanes to keep than the select kernel looked for
-            if (open && __any_sync(0xffffffffu, real && par == 0u)) {
+            if (open && __any_sync(0xffffffffu, alive)) {
                 if (lane == 0 && atomicExch(sp.flags + f, 1) == 0) sp.list[atomicAdd(sp.ctrs, 1u)] = (int)f;
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(kempty0 + 8u * kslot);
+        if (lane == 0) mbar_arrive(kempty0 + 8u * my_kslot);
     }
 }
 

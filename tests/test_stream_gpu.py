@@ -164,6 +164,23 @@ def test_repeated_launches_are_identical_and_correct(cuda_device, N, n_off, top_
             assert all(torch.equal(a, b) for a, b in zip(out, first)), f"launch {r} differs from launch 0"
 
 
+@pytest.mark.parametrize("N,n_off", [(33, 72), (64, 36), (64, 72), (100, 36), (130, 72), (240, 36), (240, 72), (300, 36)])
+def test_small_frames_many_units_per_cta(cuda_device, N, n_off):
+    """Frames with fewer item slots than the CTA has warps: different warps of a CTA work on different frames at the same time
+    and drift apart, and with thousands of frames the kept-block ring is reused many times -- the regime in which ring
+    requests must go out in ticket order (a hang / corruption here was found and fixed in round 2)."""
+    F = 7000
+    props, scores = synth.make_frames_chunked(F, N, n_off, seed=N + n_off, device=cuda_device, groups=4)
+    ref = nms_batched(props, scores, 50.0, 8, tuning=dict(path=1, variant=_capi.FUSED_REG))
+    for tuning in (STREAM, dict(variant=3, stream_warps=16, lanes_per_pass=1), dict(variant=3, stream_warps=5), dict(variant=3, select_cap=8)):
+        for rep in range(3):
+            got = nms_batched(props, scores, 50.0, 8, tuning=tuning)
+            for x, y in zip(got, ref):
+                assert torch.equal(x, y), f"N={N} No={n_off} tuning={tuning} rep={rep}"
+    idx = torch.arange(0, F, 97)
+    assert_same([t[idx] for t in ref], oracle_batched(props[idx].cpu(), scores[idx].cpu(), 50.0, 8), f"oracle sample N={N}")
+
+
 def test_streaming_and_cluster_kernels_agree_on_a_large_batch(cuda_device):
     F = 2048
     for groups, top_k in ((8, 4), (2, 4), (3, 8)):
