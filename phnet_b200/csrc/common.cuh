@@ -193,8 +193,8 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (int i = 0; i < 16; ++i)
-        if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;   // (try_wait itself suspends the warp for a while before it gives up)
+    if (mbar_try_wait(bar, parity)) return;
     mbar_wait_slow(bar, parity);
 }
 // Debug variant: gives up after ~2^22 polls and appends {tag, block, thread, parity, a, b} to `dbg` (first word = count).

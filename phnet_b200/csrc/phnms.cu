@@ -130,12 +130,12 @@ StreamShape stream_shape(int64_t F, int64_t N, int n_off, int64_t top_k, const p
         ss.bad_tuning = true;
         return ss;
     }
-    // rows per thread: one.  (Two rows per thread at n_off 36 -- 72 offset registers either way, items twice as large -- is
-    // compiled for experiments, PHNMS_STREAM_CPT=2: measured slower, 0.64 vs 0.73 of the roofline at N = 1000, top_k = 4.)
+    // rows per thread: one.  (Two rows per thread at n_off 36 -- 72 offset registers either way, items twice as large -- was
+    // measured slower: 0.64 vs 0.73 of the roofline at N = 1000, top_k = 4.)
     ss.cpt = 1;
-    if (g_env.stream_cpt == 2 && n_off == 36) ss.cpt = 2;
     ss.lanes = t.lanes_per_pass ? t.lanes_per_pass : g_env.lanes_per_pass;
-    if (ss.lanes == 0) ss.lanes = (top_k < 0 || top_k >= 2) ? 2 : 1;
+    // measured (N = 1000): 72 offsets: 2 lanes per pass 0.86 of the roofline, 4 lanes 0.78 (spills); 36 offsets: 4 lanes 0.775, 2 lanes 0.76
+    if (ss.lanes == 0) ss.lanes = (top_k >= 0 && top_k < 2) ? 1 : ((n_off == 36 && (top_k < 0 || top_k >= 4)) ? 4 : 2);
     if (ss.lanes != 1 && ss.lanes != 2 && ss.lanes != 4) {
         ss.bad_tuning = true;
         return ss;
@@ -636,25 +636,28 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
         q.off_ring = ss.L.off_ring; q.off_slots = ss.L.off_slots; q.slot_bytes = ss.L.slot_bytes; q.off_bit = ss.L.off_bit;
         const int lanes = ss.lanes;
         int rc = 0;
-#define PHNMS_LAUNCH_STREAM(NO, NK, CP)                                                                               \
+#define PHNMS_LAUNCH_STREAM(NO, NK, GE)                                                                               \
     do {                                                                                                              \
-        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_stream_kernel<NO, NK, CP>), dev.smem_optin);        \
+        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_stream_kernel<NO, NK, GE>), dev.smem_optin);        \
         if (rc) return fail_at("stream smem attribute", rc);                                                          \
-        phnms_stream_kernel<NO, NK, CP><<<(unsigned)ss.grid, ss.warps * 32, (size_t)ss.L.total, stream>>>(q);         \
+        phnms_stream_kernel<NO, NK, GE><<<(unsigned)ss.grid, ss.warps * 32, (size_t)ss.L.total, stream>>>(q);         \
     } while (0)
-        if (n_off == 72) {
-            if (lanes == 4) PHNMS_LAUNCH_STREAM(72, 4, 1);
-            else if (lanes == 2) PHNMS_LAUNCH_STREAM(72, 2, 1);
-            else PHNMS_LAUNCH_STREAM(72, 1, 1);
-        } else if (ss.cpt == 2) {
-            if (lanes == 4) PHNMS_LAUNCH_STREAM(36, 4, 2);
-            else if (lanes == 2) PHNMS_LAUNCH_STREAM(36, 2, 2);
-            else PHNMS_LAUNCH_STREAM(36, 1, 2);
-        } else {
-            if (lanes == 4) PHNMS_LAUNCH_STREAM(36, 4, 1);
-            else if (lanes == 2) PHNMS_LAUNCH_STREAM(36, 2, 1);
-            else PHNMS_LAUNCH_STREAM(36, 1, 1);
-        }
+#define PHNMS_LAUNCH_STREAM_NO(NO)                                                                                    \
+    do {                                                                                                              \
+        if (general) {                                                                                                \
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(NO, 4, true);                                                         \
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(NO, 2, true);                                                    \
+            else PHNMS_LAUNCH_STREAM(NO, 1, true);                                                                    \
+        } else {                                                                                                      \
+            if (lanes == 4) PHNMS_LAUNCH_STREAM(NO, 4, false);                                                        \
+            else if (lanes == 2) PHNMS_LAUNCH_STREAM(NO, 2, false);                                                   \
+            else PHNMS_LAUNCH_STREAM(NO, 1, false);                                                                   \
+        }                                                                                                             \
+    } while (0)
+        const bool general = ss.nseg != 1 || ss.bundle != 1 || n_valid != nullptr;
+        if (n_off == 72) PHNMS_LAUNCH_STREAM_NO(72);
+        else PHNMS_LAUNCH_STREAM_NO(36);
+#undef PHNMS_LAUNCH_STREAM_NO
 #undef PHNMS_LAUNCH_STREAM
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail_at("stream launch", (int)e);

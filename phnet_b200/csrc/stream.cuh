@@ -170,23 +170,24 @@ __device__ __forceinline__ bool stream_eval(uint32_t s0, int cnt, const bool (&l
     return true;
 }
 
-template <int NOFF, int NKP, int CPT>
+// GEN = false: the plain big-batch case -- a unit is one whole frame (nseg == 1, bundle == 1) and there is no n_valid; everything
+// about an item follows from (us, ci) in a handful of instructions.  GEN = true: segments / bundles / ragged frames.
+template <int NOFF, int NKP, bool GEN>
 __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(const StreamParams sp) {
-    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4, RPI = 32 * CPT;   // rows per item
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4, RPI = 32;   // rows per item
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t bar_rows = smem_u32(smem) + 8u * warp;
-    const uint32_t kfull0 = smem_u32(smem) + 128u, kempty0 = smem_u32(smem) + 384u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t smem_s = smem_u32(smem);
+    const uint32_t bar_rows = smem_s + 8u * warp;
+    const uint32_t kfull0 = smem_s + 128u, kempty0 = smem_s + 384u;
     uint32_t *next_req = reinterpret_cast<uint32_t *>(smem + 640);
-    unsigned char *ring = smem + sp.off_ring;
-    unsigned char *myslot = smem + sp.off_slots + (size_t)warp * sp.slot_bytes;
-    float *sc_buf = reinterpret_cast<float *>(myslot);
-    unsigned char *rows_base = myslot + 128 * CPT;
+    const uint32_t ring_s = smem_s + (uint32_t)sp.off_ring;
+    const uint32_t slot_s = smem_s + (uint32_t)sp.off_slots + (uint32_t)warp * (uint32_t)sp.slot_bytes;   // 32 scores, then the rows
     const uint32_t ks = (uint32_t)sp.ks, ips = (uint32_t)sp.ips;
-    const int nseg = sp.nseg;
+    const int nseg = GEN ? sp.nseg : 1, bundle = GEN ? sp.bundle : 1;
 
-    if (tid == 0) {
-        for (int w = 0; w < nwarps; ++w) mbar_init(smem_u32(smem) + 8u * w, 33);   // 1 expect_tx arrive + 32 cp.async arrives
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < nwarps; ++w) mbar_init(smem_s + 8u * w, 33);   // 1 expect_tx arrive + 32 cp.async arrives
         for (uint32_t s = 0; s < ks; ++s) {
             mbar_init(kfull0 + 8u * s, 1);
             mbar_init(kempty0 + 8u * s, ips);   // one arrive per item slot of the unit
@@ -197,24 +198,24 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
     }
     __syncthreads();
 
-    // units of this CTA: u = b, b + G, ...; unit u = (frame u / nseg, segment u % nseg); the unit's item slots ci = 0 .. ips-1
-    // go round the warps: warp w takes the CTA's item slots w, w + nwarps, ... (tracked incrementally as (us, ci): no division
-    // on the per-item path unless a unit has fewer item slots than the CTA has warps)
-    const long long U = sp.bundle > 1 ? (sp.F + sp.bundle - 1) / sp.bundle : sp.F * nseg;
+    // Units of this CTA: u = b, b + G, ...  A unit is one frame; or, when there are fewer frames than SMs, one of nseg segments
+    // of a frame; or, for small frames, a bundle of consecutive frames (so that every warp has an item in every unit).  The
+    // unit's item slots ci = 0 .. ips-1 go round the warps: warp w takes the CTA's item slots w, w + nwarps, ..., tracked
+    // incrementally as (us, ci) -- no division on the per-item path unless a unit has fewer item slots than the CTA has warps.
+    const long long U = bundle > 1 ? (sp.F + bundle - 1) / bundle : sp.F * nseg;
     const uint32_t b = blockIdx.x, G = gridDim.x;
     const uint32_t nu = b < U ? (uint32_t)((U - b + G - 1) / G) : 0u;
     const int look = (int)ks - 2;
-    const uint32_t ring_slot = (uint32_t)sp.block_bytes * (uint32_t)(sp.bundle > 1 ? sp.bundle : 1);
+    const uint32_t ring_slot = (uint32_t)sp.block_bytes * (uint32_t)(bundle > 1 ? bundle : 1);
     if (nu == 0u) return;
 
-    struct Item { long long f; int r0, nrows, fb; bool valid; };
-    const int bundle = sp.bundle;
-    auto decode = [&](uint32_t us, uint32_t ci) {
+    struct Item { long long f; int r0, fb; bool valid; };
+    auto locate = [&](uint32_t us, uint32_t ci) {
         Item it;
         const long long u = (long long)b + (long long)us * G;
         int c;
         it.fb = 0;
-        if (bundle > 1) {          // unit = frames u * bundle .. ; item slot ci = (frame within the bundle, item of the frame)
+        if (bundle > 1) {          // unit = frames u * bundle ..; item slot ci = (frame within the bundle, item of the frame)
             it.fb = (int)(ci / (uint32_t)sp.ipf);
             c = (int)ci - it.fb * sp.ipf;
             it.f = u * bundle + it.fb;
@@ -227,61 +228,42 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
             it.valid = c < sp.ipf;
         }
         it.r0 = c * RPI;
-        int nv = sp.N;
-        if (sp.n_valid) nv = max(0, min(sp.n_valid[it.f], sp.N));
-        it.nrows = it.valid ? max(0, min(nv - it.r0, RPI)) : 0;
         return it;
     };
-    auto advance = [&](uint32_t &us, uint32_t &ci, uint32_t &kslot, uint32_t &kpar) {
-        ci += (uint32_t)nwarps;
-        if (ci >= ips) {
-            uint32_t d = 1u;
-            if (ips >= (uint32_t)nwarps) {
-                ci -= ips;
-            } else {
-                d = ci / ips;
-                ci -= d * ips;
-            }
-            us += d;
-            kslot += d;
-            while (kslot >= ks) {
-                kslot -= ks;
-                kpar ^= 1u;
-            }
-        }
+    auto rows_of = [&](const Item &it) {
+        int nv = sp.N;
+        if (GEN && sp.n_valid) nv = max(0, min(sp.n_valid[it.f], sp.N));
+        return it.valid ? max(0, min(nv - it.r0, RPI)) : 0;
     };
     // the item's rows -> this warp's slot.  Row data keeps its global address modulo 16 (rows are only 4-byte aligned:
     // 308 / 164 bytes), so the aligned body is one bulk copy and at most 3 words at either end are copied singly.
-    auto issue = [&](const Item &it) {
-        if (it.nrows <= 0) return;
+    auto issue = [&](const Item &it, int nrows) {
+        if (nrows <= 0) return;
         const float *src = sp.props + ((size_t)it.f * sp.N + it.r0) * P;
-        const float *ssrc = sp.scores + (size_t)it.f * sp.N + it.r0;
         const uintptr_t a0 = (uintptr_t)src;
-        const uint32_t bytes = (uint32_t)it.nrows * (P * 4);
+        const uint32_t bytes = (uint32_t)nrows * (P * 4);
         if (((a0 | bytes) & 15u) == 0u) {   // the usual case: N a multiple of 4 and an aligned tensor
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar_rows, bytes);
-                bulk_g2s(smem_u32(rows_base), src, bytes, bar_rows);
+                bulk_g2s(slot_s + 128u, src, bytes, bar_rows);
             }
         } else {
             const uintptr_t b0 = (a0 + 15) & ~(uintptr_t)15, e0 = (a0 + bytes) & ~(uintptr_t)15;
-            unsigned char *D = rows_base + (a0 & 15);
+            const uint32_t D = slot_s + 128u + (uint32_t)(a0 & 15);
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar_rows, (uint32_t)(e0 - b0));
-                bulk_g2s(smem_u32(D + (b0 - a0)), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
+                bulk_g2s(D + (uint32_t)(b0 - a0), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
             }
             const int hw = (int)((b0 - a0) >> 2), tw = (int)((a0 + bytes - e0) >> 2), t0 = (int)((e0 - a0) >> 2);
-            if (lane >= 1 && lane - 1 < hw) cp_async_4(smem_u32(D + 4 * (lane - 1)), src + (lane - 1));
-            if (lane >= 4 && lane - 4 < tw) cp_async_4(smem_u32(D + 4 * (t0 + lane - 4)), src + t0 + (lane - 4));
+            if (lane >= 1 && lane - 1 < hw) cp_async_4(D + 4u * (uint32_t)(lane - 1), src + (lane - 1));
+            if (lane >= 4 && lane - 4 < tw) cp_async_4(D + 4u * (uint32_t)(t0 + lane - 4), src + t0 + (lane - 4));
         }
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-            if (c * 32 + lane < it.nrows) cp_async_4(smem_u32(sc_buf + c * 32 + lane), ssrc + c * 32 + lane);
+        if (lane < nrows) cp_async_4(slot_s + 4u * (uint32_t)lane, sp.scores + (size_t)it.f * sp.N + it.r0 + lane);
         cp_async_mbar_arrive_noinc(bar_rows);
     };
     // kept blocks: requested up to `look` units ahead by whichever warp gets there first (lane 0 only).  Requests go out in
     // TICKET ORDER (`issued` counts them): mbarrier waits only tell even from odd phases, so nobody may get two phases ahead
-    // of a barrier -- when a frame has fewer item slots than the CTA has warps, different warps work on different units and
+    // of a barrier -- when a unit has fewer item slots than the CTA has warps, different warps work on different units and
     // drift apart; without the ordering a warp far ahead could pass the wait for "the previous user of this ring slot is
     // done" on the strength of the user before that.  A ticket waits for units older than every unit its claimer (or any warp
     // spinning on `issued`) is working on, so the oldest unfinished unit can always finish: no cycle.
@@ -308,92 +290,90 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
             const long long nb = bundle > 1 ? min((long long)bundle, sp.F - fq) : 1;   // blocks of consecutive frames are contiguous
             const uint32_t nbytes = (uint32_t)nb * (uint32_t)sp.block_bytes;
             mbar_arrive_expect_tx(kfull0 + 8u * slot, nbytes);
-            bulk_g2s(smem_u32(ring + (size_t)slot * ring_slot), sp.blocks + (size_t)fq * sp.block_bytes, nbytes, kfull0 + 8u * slot);
+            bulk_g2s(ring_s + slot * ring_slot, sp.blocks + (size_t)fq * sp.block_bytes, nbytes, kfull0 + 8u * slot);
             __threadfence_block();
             *issued = t + 1u;
         }
     };
 
-    uint32_t rphase = 0u;
-    // this warp's first item slot: (us, ci) with us * ips + ci == warp
+    // per-warp running state: (us, ci) of the next item slot to work on; ring slot / phase of unit us; phase of the row barrier
     uint32_t us = (uint32_t)warp / ips, ci = (uint32_t)warp - us * ips;
-    uint32_t kslot = us % ks, kpar = (us / ks) & 1u;
+    uint32_t kslot = us % ks, kpar = (us / ks) & 1u, rphase = 0u;
     if (us < nu) {
-        issue(decode(us, ci));
+        const Item first = locate(us, ci);
+        issue(first, rows_of(first));
         if (lane == 0) ensure_requested((long long)us + look);
     }
 
     while (us < nu) {
-        float x[CPT][NOFF];
-        int st[CPT], en[CPT], nrows;
-        float score[CPT];
-        long long f;
-        int r0, fb;
-        bool valid;
-        const uint32_t my_kslot = kslot, my_kpar = kpar, us_item = us;
+        float x[1][NOFF];
+        int st[1], en[1], nrows;
+        float score;
+        const uint32_t it_us = us, it_ci = ci, it_k = kslot | (kpar << 8);   // all that identifies this item across the evaluation
         {
-            const Item cur = decode(us, ci);
-            f = cur.f;
-            nrows = cur.nrows;
-            valid = cur.valid;
-            r0 = cur.r0;
-            fb = cur.fb;
+            const Item cur = locate(us, ci);
+            nrows = rows_of(cur);
             if (nrows > 0) {
                 mbar_wait(bar_rows, rphase);
                 rphase ^= 1u;
-                const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)f * sp.N + r0) * P);
-                const float *rows = reinterpret_cast<const float *>(rows_base + (a0 & 15));
+                const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)cur.f * sp.N + cur.r0) * P);
+                const uint32_t row = slot_s + 128u + (uint32_t)(a0 & 15) + (uint32_t)(lane < nrows ? lane : 0) * (P * 4);
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const int rr = c * 32 + lane < nrows ? c * 32 + lane : 0;
-                    const float *row = rows + (size_t)rr * P;
-#pragma unroll
-                    for (int i = 0; i < NOFF; ++i) x[c][i] = row[5 + i];
-                    st[c] = lane_start(row[2], NOFF);          // nms_kernel.cu:29-30
-                    en[c] = lane_end(row[4], st[c], NOFF);     // :32-34
-                    score[c] = sc_buf[rr];
-                }
+                for (int i = 0; i < NOFF; ++i) x[0][i] = __uint_as_float(lds_u32(row + 4u * (5 + i)));
+                st[0] = lane_start(__uint_as_float(lds_u32(row + 8u)), NOFF);            // nms_kernel.cu:29-30
+                en[0] = lane_end(__uint_as_float(lds_u32(row + 16u)), st[0], NOFF);      // :32-34
+                score = __uint_as_float(lds_u32(slot_s + 4u * (uint32_t)(lane < nrows ? lane : 0)));
             } else {
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-#pragma unroll
-                    for (int i = 0; i < NOFF; ++i) x[c][i] = 0.0f;
-                    st[c] = 0;
-                    en[c] = -1;
-                    score[c] = 0.0f;
+                for (int i = 0; i < NOFF; ++i) x[0][i] = 0.0f;
+                st[0] = 0;
+                en[0] = -1;
+                score = 0.0f;
+            }
+            __syncwarp();   // every lane has read its row: the slot is free for the next item
+            // advance to this warp's next item slot and request it
+            ci += (uint32_t)nwarps;
+            if (ci >= ips) {
+                uint32_t d = 1u;
+                if (ips >= (uint32_t)nwarps) {
+                    ci -= ips;
+                } else {
+                    d = ci / ips;
+                    ci -= d * ips;
+                }
+                us += d;
+                kslot += d;
+                while (kslot >= ks) {
+                    kslot -= ks;
+                    kpar ^= 1u;
                 }
             }
-            __syncwarp();   // every lane has read its rows: the slot is free for the next item
-            const uint32_t us_cur = us;
-            advance(us, ci, kslot, kpar);
-            if (us < nu) issue(decode(us, ci));
-            if (lane == 0) ensure_requested((long long)us_cur + look);
+            if (us < nu) {
+                const Item nxt = locate(us, ci);
+                issue(nxt, rows_of(nxt));
+            }
+            if (lane == 0) ensure_requested((long long)it_us + look);
             __syncwarp();
         }
 
         // ---- the frame's kept lanes (block written by the select kernel: {nk, open, n} + slots) -------------------------------
-        spin_until_issued(us_item);   // (the request of this unit's block has gone out: the parity below names the right phase)
-        mbar_wait(kfull0 + 8u * my_kslot, my_kpar);
-        const uint32_t blk_s = smem_u32(ring) + my_kslot * ring_slot + (uint32_t)fb * (uint32_t)sp.block_bytes;
+        spin_until_issued(it_us);   // (the request of this unit's block has gone out: the parity below names the right phase)
+        mbar_wait(kfull0 + 8u * (it_k & 0xffu), it_k >> 8);
+        uint32_t blk_s = ring_s + (it_k & 0xffu) * ring_slot;
+        if (bundle > 1) blk_s += (it_ci / (uint32_t)sp.ipf) * (uint32_t)sp.block_bytes;
         const int nk = min((int)lds_u32(blk_s), sp.top_k);
-        const bool open = lds_u32(blk_s + 4) != 0u;
         const int nvf = (int)lds_u32(blk_s + 8);   // proposals in the frame
 
-        bool real[CPT];
-        uint32_t key[CPT];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            real[c] = c * 32 + lane < nrows;
-            key[c] = key_desc(real[c] ? score[c] : 0.0f, sp.sort_model == 1);
-        }
+        const bool real[1] = {lane < nrows};
+        uint32_t key = key_desc(real[0] ? score : 0.0f, sp.sort_model == 1);
         // (torch sort model) a frame of <= 32 proposals is ordered by ATen's unstable bitonic network -- the select kernel's
         // rank keys are then the sorted positions, and so must these be; such a frame is exactly rows 0 .. n-1 of one item
-        if (sp.sort_model == 0 && valid && nvf <= 32 && nvf >= 2 && nrows > 0) {
+        if (sp.sort_model == 0 && nvf <= 32 && nvf >= 2 && nrows > 0) {
             const int nv = nvf;
             float *bit_key = reinterpret_cast<float *>(smem + sp.off_bit + warp * 384);
             int *bit_val = reinterpret_cast<int *>(bit_key + 32), *bit_ok = bit_val + 32;
             bit_ok[lane] = lane < nv;
-            bit_key[lane] = lane < nv ? score[0] : 0.0f;
+            bit_key[lane] = lane < nv ? score : 0.0f;
             bit_val[lane] = lane < nv ? lane : 0;
             __syncwarp();
             for (unsigned size = 2; size <= 32; size *= 2) {
@@ -417,53 +397,49 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
             int mypos = 0;
             for (int q = 0; q < 32; ++q)
                 if (bit_val[q] == lane && q < nv) mypos = q;
-            key[0] = (uint32_t)mypos;
+            key = (uint32_t)mypos;
             __syncwarp();
         }
-        u64 myK[CPT];
-        uint32_t mb[CPT][MW], par[CPT];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            myK[c] = real[c] ? (((u64)key[c] << 32) | (uint32_t)(r0 + c * 32 + lane)) : kNone64;
-            par[c] = 0u;
-            range_mask<MW>(st[c], en[c], mb[c]);
-        }
+        uint32_t mb[1][MW], par[1] = {0u};
+        range_mask<MW>(st[0], en[0], mb[0]);
 
-        if (valid) {
-            if (nrows > 0) {
-                for (int k0 = 0; k0 < nk; k0 += NKP) {
-                    const int cnt = min(NKP, nk - k0);
-                    if (!stream_eval<NOFF, NKP, CPT>(blk_s + kBlkHdr + (uint32_t)k0 * SLOT, cnt, real, myK, st, en, mb, x, sp.thr, par, k0)) {
-                        // a pair with a negative common start somewhere in the warp: the exact evaluator, one lane at a time
-                        FusedParams fp;
-                        fp.thr = sp.thr;
-                        auto my_hdr = [&](int c) { return sp.props + ((size_t)f * sp.N + (uint32_t)(r0 + c * 32 + lane)) * P; };
-                        for (int k = 0; k < cnt; ++k) {
-                            const unsigned char *const h1[1] = {ring + (size_t)my_kslot * ring_slot + (size_t)fb * sp.block_bytes + kBlkHdr + (size_t)(k0 + k) * SLOT};
-                            bool hit[1][CPT];
-                            freg_eval<NOFF, CPT, 1>(fp, f, h1, real, myK, st, en, mb, x, my_hdr, par, hit, k0 + k);
-                        }
+        if (nrows > 0) {
+            // (the item's first row: it.r0 -- recomputed rather than kept in a register across the passes)
+            const u64 myK[1] = {real[0] ? (((u64)key << 32) | (uint32_t)(locate(it_us, it_ci).r0 + lane)) : kNone64};
+            for (int k0 = 0; k0 < nk; k0 += NKP) {
+                const int cnt = min(NKP, nk - k0);
+                if (!stream_eval<NOFF, NKP, 1>(blk_s + kBlkHdr + (uint32_t)k0 * SLOT, cnt, real, myK, st, en, mb, x, sp.thr, par, k0)) {
+                    // a pair with a negative common start somewhere in the warp: the exact evaluator, one lane at a time
+                    FusedParams fp;
+                    fp.thr = sp.thr;
+                    const Item cur = locate(it_us, it_ci);
+                    auto my_hdr = [&](int) { return sp.props + ((size_t)cur.f * sp.N + (uint32_t)(cur.r0 + lane)) * P; };
+                    const unsigned char *blk_g = smem + (blk_s - smem_s);
+                    for (int k = 0; k < cnt; ++k) {
+                        const unsigned char *const h1[1] = {blk_g + kBlkHdr + (size_t)(k0 + k) * SLOT};
+                        bool hit[1][1];
+                        freg_eval<NOFF, 1, 1>(fp, cur.f, h1, real, myK, st, en, mb, x, my_hdr, par, hit, k0 + k);
                     }
                 }
             }
-            // ---- outputs, written once ------------------------------------------------------------------------------------
-            bool alive = false;
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int i_out = r0 + c * 32 + lane;
+        }
+        // ---- outputs, written once ----------------------------------------------------------------------------------------
+        {
+            const Item cur = locate(it_us, it_ci);
+            if (cur.valid) {
+                const int i_out = cur.r0 + lane;
                 if (i_out < sp.N) {
-                    st_global_cs_u64(sp.parent + (size_t)f * sp.N + i_out, (long long)par[c]);
-                    if (i_out >= nk) st_global_cs_u64(sp.keep + (size_t)f * sp.N + i_out, 0ll);   // :139-140
+                    st_global_cs_u64(sp.parent + (size_t)cur.f * sp.N + i_out, (long long)par[0]);
+                    if (i_out >= nk) st_global_cs_u64(sp.keep + (size_t)cur.f * sp.N + i_out, 0ll);   // :139-140
                 }
-                alive |= real[c] && par[c] == 0u;
-            }
-            // an open frame with a proposal nobody covers has more lanes to keep than the select kernel looked for
-            if (open && __any_sync(0xffffffffu, alive)) {
-                if (lane == 0 && atomicExch(sp.flags + f, 1) == 0) sp.list[atomicAdd(sp.ctrs, 1u)] = (int)f;
+                // an open frame with a proposal nobody covers has more lanes to keep than the select kernel looked for
+                if (lds_u32(blk_s + 4) != 0u && __any_sync(0xffffffffu, real[0] && par[0] == 0u)) {
+                    if (lane == 0 && atomicExch(sp.flags + cur.f, 1) == 0) sp.list[atomicAdd(sp.ctrs, 1u)] = (int)cur.f;
+                }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(kempty0 + 8u * my_kslot);
+        if (lane == 0) mbar_arrive(kempty0 + 8u * (it_k & 0xffu));
     }
 }
 
