@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--groups", type=int, default=8, help="lane groups per synthetic frame (2-4 = road-like; PHNet max_lanes is 4)")
+    ap.add_argument("--outlier-frac", type=float, default=0.1, help="fraction of proposals that belong to no lane group")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 2 register-resident cluster kernel, 3 streaming path")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA op (oracle/_ref)")
     return ap.parse_args()
 
 
@@ -62,7 +66,8 @@ def algorithmic_bytes_per_frame(N: int, n_off: int) -> int:
 
 def workload_name(a) -> str:
     return (f"lane NMS, {a.proposals} proposals x {a.offsets} offsets fp32 per frame, overlap {a.overlap:g}, top_k {a.top_k} "
-            f"(BASELINE configs[1] frame shape; batch scaled to {a.frames} frames/GPU/step so inputs exceed L2)")
+            f"(BASELINE configs[1] frame shape; batch scaled to {a.frames} frames/GPU/step so inputs exceed L2; "
+            f"generator: {a.groups} lane groups per frame, {a.outlier_frac:g} outliers)")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -130,15 +135,45 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(N, n_off, frames):
-    """dram bytes per launch from the committed ncu --set full capture, scaled per frame (profiles/roofline_traffic.json)."""
+def ncu_traffic(N, n_off, top_k, frames):
+    """DRAM bytes per call from the committed `ncu --set full` captures of the same kernels, scaled per frame
+    (profiles/roofline_traffic.json).  STATIC: a hardware counter cannot be read inside this run, so the figure is the
+    capture's, not this run's -- the line says so in `traffic_source`."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             t = json.load(f)
-        key = f"N{N}_No{n_off}"
-        return float(t[key]["dram_bytes_per_frame"]) * frames
+        e = t[f"N{N}_No{n_off}_k{top_k}"]
+        return float(e["dram_bytes_per_frame"]) * frames, "static: " + e["source"]
     except Exception:
-        return None
+        return None, "no committed capture for this shape"
+
+
+def ref_cuda_op_rate(a, dev, frames=256):
+    """frames/s of the reference's OWN CUDA op (libs/ops/csrc/nms_kernel.cu:147-192 via oracle/_ref), called per frame the
+    way get_lanes calls it (libs/models/Router4OL.py:460-465), including the `keep[:num_to_keep]` host sync.  None when
+    oracle/_ref was not built (it needs /root/reference at build time)."""
+    try:
+        import torch
+        from oracle import ref_op
+        from phnet_b200 import synth
+        if ref_op.path(a.offsets) is None:
+            return None
+        props, scores = synth.make_frames(frames, a.proposals, a.offsets, seed=a.seed + 7, groups=a.groups, outlier_frac=a.outlier_frac)
+        p, s = props.to(dev), scores.to(dev)
+        for i in range(8):
+            k, n, _ = ref_op.nms(p[i], s[i], a.overlap, a.top_k)
+            _ = k[:n]
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(frames):
+            k, n, _ = ref_op.nms(p[i], s[i], a.overlap, a.top_k)
+            _ = k[:n]
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        return {"value": frames / dt, "unit": UNIT, "kind": "reference CUDA op (oracle/_ref), one call per frame + keep[:num] sync",
+                "sample": f"{frames} frames in {dt:.2f} s"}
+    except Exception as e:   # noqa: BLE001 -- a reported extra, never fatal
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -146,7 +181,7 @@ def cpu_oracle_rate(a, frames, threads, repeat=1):
     """frames/s of the CPU oracle (literal reference algorithm: full 64x64-tile bitmask + serial collect)."""
     from oracle import oracle
     from phnet_b200 import synth
-    props, scores = synth.make_frames(frames, a.proposals, a.offsets, seed=a.seed + 991)
+    props, scores = synth.make_frames(frames, a.proposals, a.offsets, seed=a.seed + 991, groups=a.groups, outlier_frac=a.outlier_frac)
     p, s = props.numpy(), scores.numpy()
     best = None
     for _ in range(repeat):
@@ -169,7 +204,7 @@ def run_reference(a):
     cores = oracle.max_threads()
     probe_rate, _ = cpu_oracle_rate(a, max(cores, 8), cores)
     sample = max(cores, int(probe_rate * 1.0))                   # about one second of host work per step
-    props, scores = synth.make_frames(sample, a.proposals, a.offsets, seed=a.seed)
+    props, scores = synth.make_frames(sample, a.proposals, a.offsets, seed=a.seed, groups=a.groups, outlier_frac=a.outlier_frac)
     p, s = props.numpy(), scores.numpy()
     for _ in range(a.warmup):
         oracle.nms_batched(p, s, None, a.overlap, a.top_k, lazy=False, threads=cores)
@@ -219,11 +254,12 @@ def run_ours(a):
     _capi.lib()  # fail loudly before allocating anything if the native library is missing
 
     N, n_off, F = a.proposals, a.offsets, a.frames
-    tune = _capi.tuning(path=a.path, cluster=a.cluster, threads=a.threads, max_clusters=a.max_clusters)
-    plan = _capi.plan(F, N, n_off, tune)
+    tune = _capi.tuning(path=a.path, cluster=a.cluster, threads=a.threads, max_clusters=a.max_clusters, variant=a.variant)
+    plan = _capi.plan(F, N, n_off, tune, a.top_k)
 
     # synthetic frames, generated on the device rank by rank (weak scaling: every rank owns `F` frames)
-    props, scores = synth.make_frames_chunked(F, N, n_off, seed=a.seed * 1000 + rank, device=dev)
+    props, scores = synth.make_frames_chunked(F, N, n_off, seed=a.seed * 1000 + rank, device=dev, groups=a.groups,
+                                              outlier_frac=a.outlier_frac)
     outs = [(torch.empty((F, N), dtype=torch.int64, device=dev), torch.empty((F,), dtype=torch.int64, device=dev),
              torch.empty((F, N), dtype=torch.int64, device=dev)) for _ in range(2)]
     gathered = [None]
@@ -243,8 +279,9 @@ def run_ours(a):
         try:
             from phnet_b200 import peer
             collector = peer.PeerCollector(F, a.top_k + 1, nbuf=nbuf)
-            collection = (f"records stored into every rank's buffer over peer memory (CUDA IPC + NVLink) by the op itself; one flag "
-                          f"kernel per step signals this step and waits for step e-{lag} of all ranks ({nbuf} rotating buffers)")
+            collection = (f"records stored into every rank's buffer over peer memory (CUDA IPC + NVLink) by the op's record kernel, whose "
+                          f"last block also signals this step and waits for step e-{lag} of all ranks ({nbuf} rotating buffers): "
+                          f"one extra launch per step")
         except Exception as e:   # noqa: BLE001 -- report why, fall back to the collective
             mode = "nccl"
             collection = f"NCCL all_gather_into_tensor per step (peer memory unavailable: {type(e).__name__}: {e})"
@@ -260,18 +297,18 @@ def run_ours(a):
         if ev_pair is not None:
             ev_pair[0].record(cur)
         if collector is not None:
-            nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b], collect=collector.collect_arg(e % nbuf))
+            # Records of step e go to every rank; the same launch signals epoch e and waits until epoch e-lag of all ranks is
+            # complete (a consumer of the gathered results runs `lag` steps behind the producer, which absorbs the
+            # step-to-step jitter between GPUs).  A rank can run at most lag + 1 steps ahead of the slowest one and a
+            # consumer reads records that are lag + 1 steps old, so 2 * lag + 3 rotating buffers guarantee that nobody
+            # overwrites records a peer has yet to read.
+            nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b],
+                        collect=collector.collect_arg(e % nbuf, signal_epoch=e, wait_epoch=max(e - lag, 0)))
         else:
             nms_batched(props, scores, a.overlap, a.top_k, tuning=tune, out=outs[b])
         if ev_pair is not None:
             ev_pair[1].record(cur)
         if collector is not None:
-            # Records of step e are on their way to every rank; those of step e-lag are complete everywhere when this
-            # returns (a consumer of the gathered results runs `lag` steps behind the producer, which absorbs the
-            # step-to-step jitter between GPUs).  A rank can run at most lag + 1 steps ahead of the slowest one (it waits
-            # for epoch e - lag of everybody) and a consumer reads records that are lag + 1 steps old, so 2 * lag + 3
-            # rotating buffers guarantee that nobody overwrites records a peer has yet to read.
-            collector._sync(e, max(e - lag, 0), 10.0)
             if ev_pair is not None and len(ev_pair) > 2:
                 ev_pair[2].record(cur)
             if e > lag:
@@ -302,7 +339,9 @@ def run_ours(a):
         e1.record()
         fence()
     ms_total = e0.elapsed_time(e1)
-    kern_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in pairs)
+    kern_all = sorted(p[0].elapsed_time(p[1]) for p in pairs)
+    kern_ms = statistics.mean(kern_all)
+    kern_median, kern_min = statistics.median(kern_all), kern_all[0]
     sync_ms = statistics.mean(p[1].elapsed_time(p[2]) for p in pairs) if collector is not None else 0.0
     gap_ms = statistics.mean(pairs[i][1].elapsed_time(pairs[i + 1][0]) for i in range(a.steps - 1)) if a.steps > 1 else 0.0
     per_rank = None
@@ -322,6 +361,23 @@ def run_ours(a):
         mine = sharding.pack_kept(outs[(a.steps - 1) & 1][0], outs[(a.steps - 1) & 1][1], a.top_k)
         assert torch.equal(last[rank * F:(rank + 1) * F], mine), "collected records differ from this rank's keep / num"
         assert bool((last[:, a.top_k] >= 1).all()), "a rank's records are missing from the gathered buffer"
+        # every OTHER rank's records, too: one NCCL all-gather of the same packed results (outside the timed region) must
+        # reproduce the peer-gathered buffer on every rank
+        via_nccl = sharding.gather_kept(mine, F * world)
+        assert torch.equal(via_nccl, last), f"rank {rank}: peer-memory collection differs from the NCCL all-gather of the same step"
+        verified = "peer-gathered buffer == NCCL all-gather of every rank's records, on every rank"
+    elif mode == "nccl":
+        verified = "NCCL all-gather (the collection itself)"
+    else:
+        verified = None
+    if rank == 0 and not a.no_cpu_baseline:
+        # and the results themselves against the oracle, on a sample of this rank's frames
+        from oracle import oracle as _oracle
+        idx = torch.arange(0, F, max(1, F // 48))[:48]
+        wk, wn, wp = _oracle.nms_batched(props[idx].cpu().numpy(), scores[idx].cpu().numpy(), None, a.overlap, a.top_k)
+        o = outs[(a.steps - 1) & 1]
+        assert (o[0][idx].cpu().numpy() == wk).all() and (o[1][idx].cpu().numpy() == wn).all() and (o[2][idx].cpu().numpy() == wp).all(), \
+            "bench results differ from the CPU oracle"
     if world > 1:
         t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -345,8 +401,8 @@ def run_ours(a):
         e2e_steps = max(3, min(a.steps, 20))
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(e2e_steps):
-            pipe(props_h, scores_h, a.overlap, a.top_k, out=out_h, tuning=tune)
+        for _ in range(e2e_steps):     # (sync=False: steps overlap; the event below waits for the last device-to-host copy)
+            pipe(props_h, scores_h, a.overlap, a.top_k, out=out_h, tuning=tune, sync=False)
         s1.record()
         fence()
         ms_e2e = s0.elapsed_time(s1)
@@ -363,6 +419,9 @@ def run_ours(a):
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample ------------------------------------------
     cpu = None
+    ref_cuda = None
+    if rank == 0 and world == 1 and not a.no_ref_cuda:
+        ref_cuda = ref_cuda_op_rate(a, dev)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle
         cores = oracle.max_threads()
@@ -376,28 +435,35 @@ def run_ours(a):
         peak, peak_src = measured_hbm_peak()
         bpf = algorithmic_bytes_per_frame(N, n_off)
         achieved = F * bpf / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(N, n_off, a.top_k, F)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "frames_per_gpu_per_step": F, "global_frames_per_step": F * world,
                        "proposals": N, "offsets": n_off, "overlap": a.overlap, "top_k": a.top_k,
+                       "groups": a.groups, "outlier_frac": a.outlier_frac,
                        "l2": f"inputs are {F * N * (6 + n_off) * 4 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
                        "parallelism": f"frames sharded x{world}; no data-path collective; kept lanes collected on every rank once per step" if world > 1 else "single GPU",
-                       "collection": collection, "per_rank": per_rank,
+                       "collection": collection, "collection_verified": verified, "per_rank": per_rank,
                        "plan": plan},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(N, n_off, F), "peak_source": peak_src,
-                         "algorithmic_bytes_per_frame": bpf, "kernel": ("phnms_topm_kernel + phnms_freg_kernel (one C-ABI call; freg is >90 % of it, profiles/)" if plan.get("variant") == 2
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_frame": bpf,
+                         "kernel": ("phnms_select_kernel + phnms_stream_kernel + resume pass (one C-ABI call; the stream kernel is ~90 % of it, profiles/)" if plan.get("variant") == 3
+                                    else "phnms_topm_kernel + phnms_freg_kernel (one C-ABI call)" if plan.get("variant") == 2
                                     else "phnms_fused_kernel" if plan["path"] == 1 else "phnms_order/mask/scan kernels"),
-                         "kernel_ms_per_launch": kern_ms},
+                         "kernel_ms_per_launch": kern_ms, "kernel_ms_median": kern_median, "kernel_ms_min": kern_min,
+                         "frac_median": F * bpf / (kern_median * 1e-3) / 1e9 / peak, "frac_best": F * bpf / (kern_min * 1e-3) / 1e9 / peak},
             "clocks": clocks.summary(),
-            "gpu_launches": a.steps * (plan["launches"] + (2 if collector is not None else 0)),
+            "gpu_launches": a.steps * (plan["launches"] + (1 if collector is not None else 0)),
         }
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if ref_cuda is not None:
+            line["ref_cuda_op"] = ref_cuda
         if world > 1:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)

@@ -186,6 +186,16 @@ typedef struct phnms_collect {
     int64_t row0;                     /* row of this call's frame 0 in every destination               */
     int64_t rows;                     /* rows of every destination: row0 + F must not exceed it        */
     int64_t *dst[PHNMS_MAX_DST];      /* device-accessible [rows, width] int64 buffers, 8-byte aligned   */
+    /* Optional completion across GPUs in the SAME launch (see phnms_peer_sync for the flag protocol): when signal_epoch or
+     * wait_epoch is non-zero, the last block of the record kernel stores signal_epoch to signal_dst[d] (d < n_dst: this
+     * rank's slot in rank d's flag array; system-scope release, after all record stores) and then waits until
+     * wait_src[r] >= wait_epoch for all r < n_dst.  sync_counter: one device uint32, zero before the first call (the kernel
+     * leaves it zero).  All zero / NULL: records only. */
+    uint64_t signal_epoch, wait_epoch, timeout_ns;
+    uint64_t *signal_dst[PHNMS_MAX_DST];
+    const uint64_t *wait_src;
+    int *status;
+    uint32_t *sync_counter;
 } phnms_collect;
 
 int phnms_forward_collect_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N,

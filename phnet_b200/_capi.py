@@ -45,7 +45,10 @@ class Plan(ctypes.Structure):
 class Collect(ctypes.Structure):
     """phnms_collect: where the compact kept-lane records of a call go (include/phnms.h)."""
     _fields_ = [("n_dst", ctypes.c_int), ("width", ctypes.c_int), ("row0", ctypes.c_int64), ("rows", ctypes.c_int64),
-                ("dst", ctypes.c_void_p * MAX_DST)]
+                ("dst", ctypes.c_void_p * MAX_DST),
+                ("signal_epoch", ctypes.c_uint64), ("wait_epoch", ctypes.c_uint64), ("timeout_ns", ctypes.c_uint64),
+                ("signal_dst", ctypes.c_void_p * MAX_DST), ("wait_src", ctypes.c_void_p), ("status", ctypes.c_void_p),
+                ("sync_counter", ctypes.c_void_p)]
 
 
 def collect(dst_ptrs, rows: int, width: int, row0: int = 0) -> Collect:

@@ -425,25 +425,70 @@ int fused_occupancy_query(const phnms_plan &pl, int n_off) {
 }
 
 // Compact kept-lane records: one thread per (frame, column) reads keep / num_keep of the call that has just been enqueued
-// and stores the value to every destination (local memory or peer GPUs' buffers, then over NVLink).  A separate 2 us
-// launch rather than an epilogue of the NMS kernels: the register-resident kernel sits exactly at its 128-register cap and
-// any addition to it costs spills in its frame loop (measured: -16 %).
+// and stores the value to every destination (local memory or peer GPUs' buffers, then over NVLink).  A separate small
+// launch after the NMS kernels (the resume pass may still rewrite a frame's keep / num_keep).  Optionally the SAME launch
+// completes the step across GPUs: the last block to finish its stores (device-wide counter) releases this rank's epoch
+// flag in every peer (system-scope release, ordered after all record stores of the grid) and then waits for an epoch of
+// all ranks -- one launch per step instead of records + flag kernel.
 struct CollectArgs {
     int n;
     long long row0;
     long long *dst[kMaxCollectDst];
+    // completion (all optional)
+    unsigned int *counter;                       // device word, zero between launches (reset by the last block)
+    unsigned long long signal_epoch, wait_epoch, timeout_ns;
+    unsigned long long *signal_dst[kMaxCollectDst];
+    const unsigned long long *wait_src;
+    int *status;
+    int n_flags;                                 // ranks taking part in the completion
+    __device__ int n_sync() const { return n_flags; }
 };
+
+__device__ __forceinline__ void peer_signal_and_wait(int t, int n, unsigned long long signal_epoch, unsigned long long *const *signal_dst,
+                                                     unsigned long long wait_epoch, const unsigned long long *wait_src,
+                                                     unsigned long long timeout_ns, int *status) {
+    if (t >= n) return;
+    if (signal_epoch) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(signal_dst[t]), "l"(signal_epoch) : "memory");
+    }
+    if (wait_epoch) {
+        unsigned long long t0, now, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_src + t) : "memory");
+            if (v >= wait_epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) {
+                if (status) atomicExch(status, 1 + t);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+}
 
 __global__ void phnms_collect_kernel(const long long *__restrict__ keep, const long long *__restrict__ num, long long F,
                                      int N, int top_k, CollectArgs ca) {
     const int w = top_k + 1;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= F * w) return;
-    const long long f = i / w;
-    const int c = (int)(i - f * w);
-    const long long cnt = num[f];
-    const long long v = c == w - 1 ? cnt : ((c < cnt && c < N) ? keep[f * N + c] : 0ll);
-    for (int d = 0; d < ca.n; ++d) ca.dst[d][(ca.row0 + f) * w + c] = v;
+    if (i < F * w) {
+        const long long f = i / w;
+        const int c = (int)(i - f * w);
+        const long long cnt = num[f];
+        const long long v = c == w - 1 ? cnt : ((c < cnt && c < N) ? keep[f * N + c] : 0ll);
+        for (int d = 0; d < ca.n; ++d) ca.dst[d][(ca.row0 + f) * w + c] = v;
+    }
+    if (ca.counter == nullptr) return;
+    // the last block to get here has seen every other block's stores (fence + atomic): it speaks for the grid
+    __shared__ int last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ca.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *ca.counter = 0u;
+    peer_signal_and_wait((int)threadIdx.x, ca.n_sync(), ca.signal_epoch, ca.signal_dst, ca.wait_epoch, ca.wait_src, ca.timeout_ns, ca.status);
 }
 
 // Cross-GPU completion of a collection step.  Every rank owns a flag array (one u64 per rank) in peer-mapped memory.
@@ -459,26 +504,7 @@ struct PeerSyncArgs {
 };
 
 __global__ void phnms_peer_sync_kernel(PeerSyncArgs a) {
-    const int t = threadIdx.x;
-    if (t >= a.n) return;
-    if (a.signal_epoch) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.signal_dst[t]), "l"(a.signal_epoch) : "memory");
-    }
-    if (a.wait_epoch) {
-        unsigned long long t0, now, v;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_src + t) : "memory");
-            if (v >= a.wait_epoch) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > a.timeout_ns) {
-                if (a.status) atomicExch(a.status, 1 + t);
-                break;
-            }
-            __nanosleep(200);
-        }
-    }
+    peer_signal_and_wait((int)threadIdx.x, a.n, a.signal_epoch, a.signal_dst, a.wait_epoch, a.wait_src, a.timeout_ns, a.status);
 }
 
 }  // namespace
@@ -579,6 +605,28 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
     ca.n = collect->n_dst;
     ca.row0 = collect->row0;
     for (int d = 0; d < kMaxCollectDst; ++d) ca.dst[d] = d < collect->n_dst ? reinterpret_cast<long long *>(collect->dst[d]) : nullptr;
+    ca.counter = nullptr;
+    ca.signal_epoch = ca.wait_epoch = 0ull;
+    ca.timeout_ns = 0ull;
+    ca.wait_src = nullptr;
+    ca.status = nullptr;
+    ca.n_flags = 0;
+    for (int d = 0; d < kMaxCollectDst; ++d) ca.signal_dst[d] = nullptr;
+    if (collect->signal_epoch || collect->wait_epoch) {   // completion across GPUs folded into the same launch
+        if (!collect->sync_counter || ((uintptr_t)collect->sync_counter & 3u)) return PHNMS_ERR_BAD_ARG;
+        if (collect->wait_epoch && !collect->wait_src) return PHNMS_ERR_BAD_ARG;
+        ca.counter = collect->sync_counter;
+        ca.signal_epoch = collect->signal_epoch;
+        ca.wait_epoch = collect->wait_epoch;
+        ca.timeout_ns = collect->timeout_ns ? collect->timeout_ns : 10000000000ull;
+        ca.wait_src = reinterpret_cast<const unsigned long long *>(collect->wait_src);
+        ca.status = collect->status;
+        ca.n_flags = collect->n_dst;
+        for (int d = 0; d < collect->n_dst; ++d) {
+            if (collect->signal_epoch && (!collect->signal_dst[d] || ((uintptr_t)collect->signal_dst[d] & 7u))) return PHNMS_ERR_BAD_ARG;
+            ca.signal_dst[d] = reinterpret_cast<unsigned long long *>(collect->signal_dst[d]);
+        }
+    }
     const long long total = (long long)F * (top_k + 1);
     phnms_collect_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
         reinterpret_cast<const long long *>(keep), reinterpret_cast<const long long *>(num_keep), F, (int)N, (int)top_k, ca);

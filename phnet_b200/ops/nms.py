@@ -47,7 +47,13 @@ def _check_inputs(boxes: torch.Tensor, scores: torch.Tensor, batched: bool):
     if boxes.shape[-1] < 6:
         raise RuntimeError("Wrong number of offsets. Rows are 5 + n_offsets wide")
     if scores.dtype != torch.float32 and boxes.dtype == torch.float32:
-        scores = scores.float()          # the reference sorts whatever dtype it is given; order is unchanged
+        # The reference sorts whatever dtype it is given (`scores.sort(0, True)`, nms.cpp:51); a cast to fp32 could merge scores
+        # that differ only beyond fp32 precision and change the order.  So: torch's own sort of the original dtype, then fp32
+        # stand-in scores that encode that order exactly (-rank: distinct, exact below 2^24 entries).
+        order = scores.sort(-1, True)[1]
+        ranks = torch.empty_like(order)
+        ranks.scatter_(-1, order, torch.arange(scores.shape[-1], device=scores.device).expand_as(order).contiguous())
+        scores = -ranks.to(torch.float32)
     if not scores.is_contiguous():
         scores = scores.contiguous()     # `scores.sort` accepts strided input (nms.cpp:51)
     if scores.shape != boxes.shape[:-1]:

@@ -35,7 +35,10 @@ class HostLaneNMS:
                 torch.empty((F,), dtype=torch.int64).pin_memory(),
                 torch.empty((F, self.N), dtype=torch.int64).pin_memory())
 
-    def __call__(self, props_h: torch.Tensor, scores_h: torch.Tensor, overlap, top_k, out=None, tuning=None):
+    def __call__(self, props_h: torch.Tensor, scores_h: torch.Tensor, overlap, top_k, out=None, tuning=None, sync: bool = True):
+        """Returns (keep, num_to_keep, parent) as pinned host tensors.  sync=True (default): the results are complete when the
+        call returns.  sync=False: the device-to-host copies may still be in flight -- the current CUDA stream has been made to
+        wait for them, so synchronise that stream (or record an event on it) before reading the tensors on the host."""
         if props_h.is_cuda or scores_h.is_cuda:
             raise RuntimeError("HostLaneNMS takes host tensors; call phnet_b200.ops.nms_batched for device tensors")
         if props_h.dtype != torch.float32 or props_h.dim() != 3 or tuple(props_h.shape[1:]) != (self.N, self.P):
@@ -81,6 +84,8 @@ class HostLaneNMS:
             self.launches += 1
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_run)
+        if sync:
+            self.s_out.synchronize()
         return keep_h, num_h, par_h
 
 
@@ -90,6 +95,4 @@ def nms_host(props_h: torch.Tensor, scores_h: torch.Tensor, overlap, top_k, devi
         k, n, p = nms_host(props_h[None], scores_h[None], overlap, top_k, device, 1)
         return [k[0], n[0], p[0]]
     pipe = HostLaneNMS(props_h.shape[1], props_h.shape[2] - 5, min(chunk_frames, max(1, props_h.shape[0])), device)
-    out = pipe(props_h, scores_h, overlap, top_k)
-    torch.cuda.current_stream(pipe.dev).synchronize()
-    return out
+    return pipe(props_h, scores_h, overlap, top_k, sync=True)

@@ -103,9 +103,20 @@ class PeerCollector:
         """0, or 1 + the rank whose signal a wait gave up on (timeout)."""
         return int(self._mem[(self.flag_off + 8 * _capi.MAX_DST) // 8].item()) & 0xffffffff
 
-    def collect_arg(self, buf: int) -> _capi.Collect:
-        return _capi.collect([b + buf * self.buf_bytes for b in self.base], rows=self.world * self.rows, width=self.width,
-                             row0=self.rank * self.rows)
+    def collect_arg(self, buf: int, signal_epoch: int = 0, wait_epoch: int = 0, timeout_s: float = 10.0) -> _capi.Collect:
+        """Descriptor for nms_batched(..., collect=...).  With signal_epoch / wait_epoch the record kernel itself completes
+        the step across GPUs (its last block releases this rank's flag in every peer, then waits for wait_epoch of all
+        ranks): one launch per step instead of records + phnms_peer_sync."""
+        c = _capi.collect([b + buf * self.buf_bytes for b in self.base], rows=self.world * self.rows, width=self.width,
+                          row0=self.rank * self.rows)
+        if signal_epoch or wait_epoch:
+            c.signal_epoch, c.wait_epoch, c.timeout_ns = int(signal_epoch), int(wait_epoch), int(timeout_s * 1e9)
+            for r, b in enumerate(self.base):
+                c.signal_dst[r] = b + self.flag_off + 8 * self.rank
+            c.wait_src = self.local + self.flag_off
+            c.status = self.local + self.flag_off + 8 * _capi.MAX_DST
+            c.sync_counter = self.local + self.flag_off + 8 * _capi.MAX_DST + 64
+        return c
 
     # -- completion flags ----------------------------------------------------------------------------------------
     def _sync(self, signal_epoch: int, wait_epoch: int, timeout_s: float):

@@ -26,13 +26,16 @@ def main():
     pc = peer.PeerCollector(Fr, top_k + 1, nbuf=3)
     wk, wn, _ = oracle.nms_batched(props.numpy(), scores.numpy(), None, 50.0, top_k)
     want = sharding.pack_kept(torch.from_numpy(wk), torch.from_numpy(wn), top_k)
-    for step in range(1, 7):                                           # several epochs over the three buffers
+    for step in range(1, 9):                                           # several epochs over the three buffers
         b = step % 3
         pc.gathered(b).fill_(-1)
         torch.cuda.synchronize()
         dist.barrier()
-        keep, num, _ = nms_batched(p, s, 50.0, top_k, collect=pc.collect_arg(b))
-        pc.signal_and_wait(step)
+        if step % 2:      # records, then the flag kernel
+            keep, num, _ = nms_batched(p, s, 50.0, top_k, collect=pc.collect_arg(b))
+            pc.signal_and_wait(step)
+        else:             # records + completion in one launch
+            keep, num, _ = nms_batched(p, s, 50.0, top_k, collect=pc.collect_arg(b, signal_epoch=step, wait_epoch=step))
         got = pc.gathered(b).cpu()
         assert pc.status() == 0, f"rank {rank}: wait timed out on rank {pc.status() - 1}"
         assert torch.equal(got, want), f"rank {rank} step {step}: gathered records differ from the oracle"
@@ -61,8 +64,7 @@ def main():
 
     def step_peer(i):
         epoch[0] += 1
-        nms_batched(pb, sb, 50.0, top_k, out=out, collect=pcb.collect_arg(i % 3))
-        pcb.signal_and_wait(epoch[0])
+        nms_batched(pb, sb, 50.0, top_k, out=out, collect=pcb.collect_arg(i % 3, signal_epoch=epoch[0], wait_epoch=epoch[0]))
 
     def step_nccl(i):
         nms_batched(pb, sb, 50.0, top_k, out=out)

