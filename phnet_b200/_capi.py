@@ -69,6 +69,30 @@ class PhnmsError(RuntimeError):
 
 
 _lib = None
+_shim = None
+SHIM_PATH = os.path.join(HERE, "csrc", "nms_impl.so")
+
+
+def shim():
+    """The pybind11 module `nms_impl` (csrc/nms_impl.cpp): the reference's native surface `nms_forward(boxes, scores, thresh,
+    top_k)` over libphnms.so, a few microseconds of host time per call.  None when it has not been built (the ctypes path is
+    then used; both end in the same C ABI call)."""
+    global _shim
+    if _shim is None:
+        _shim = False
+        if os.path.exists(SHIM_PATH) and not os.environ.get("PHNMS_NO_SHIM") and not os.environ.get("PHNMS_SO"):
+            import importlib.util
+            import torch  # noqa: F401  (libtorch symbols first)
+            lib()
+            try:
+                spec = importlib.util.spec_from_file_location("nms_impl", SHIM_PATH)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                if mod.abi_version() == ABI_VERSION:
+                    _shim = mod
+            except Exception:   # noqa: BLE001 -- stale or unloadable build: the ctypes path does the same work
+                _shim = False
+    return _shim or None
 
 
 def lib() -> ctypes.CDLL:

@@ -56,6 +56,46 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
     return SO
 
 
+SHIM_SRC = os.path.join(CSRC, "nms_impl.cpp")
+SHIM_SO = os.path.join(CSRC, "nms_impl.so")
+
+
+def shim_stale() -> bool:
+    if not os.path.exists(SHIM_SO):
+        return True
+    t = os.path.getmtime(SHIM_SO)
+    return any(os.path.getmtime(d) > t for d in (SHIM_SRC, os.path.join(CSRC, "..", "..", "include", "phnms.h")))
+
+
+def build_shim(force: bool = False, verbose: bool = False) -> str:
+    """The pybind11 module `nms_impl` (phnet_b200/csrc/nms_impl.cpp): the reference's native surface `nms_forward(boxes, scores,
+    thresh, top_k)` (libs/ops/csrc/nms.cpp:44-61) as a thin ATen adapter over libphnms.so.  Built in-tree with torch's
+    cpp_extension (host compiler only, ~1 min); needs libphnms.so next to it at run time ($ORIGIN rpath)."""
+    if not force and not shim_stale():
+        return SHIM_SO
+    import tempfile
+    from torch.utils.cpp_extension import load
+    if not os.path.exists(SO):
+        build()
+    tmp = tempfile.mkdtemp(prefix="phnms_shim_")
+    try:
+        os.environ.setdefault("MAX_JOBS", "4")
+        try:
+            load(name="nms_impl", sources=[SHIM_SRC], extra_cflags=["-O2"], with_cuda=True,
+                 extra_ldflags=[f"-L{CSRC}", "-l:libphnms.so", "-Wl,-rpath,\\$$ORIGIN"],
+                 build_directory=tmp, is_python_module=False, verbose=verbose)
+        except OSError:
+            pass    # built, but not loadable from the temporary directory: libphnms.so is found through $ORIGIN, i.e. next to it
+        if not os.path.exists(os.path.join(tmp, "nms_impl.so")):
+            raise RuntimeError("building the nms_impl shim failed")
+        shutil.copy(os.path.join(tmp, "nms_impl.so"), SHIM_SO)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return SHIM_SO
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    if "--shim" in sys.argv:
+        print(build_shim(force=True, verbose="-v" in sys.argv))

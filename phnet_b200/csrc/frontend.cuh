@@ -14,6 +14,7 @@
 // x_i = expf(e_i - max), out_1 = x_1 / (x_1 + x_0) -- checked bit for bit against torch.softmax on the GPU (tests).
 #pragma once
 #include "common.cuh"
+#include "select.cuh"
 
 namespace phnms {
 
@@ -107,6 +108,184 @@ __global__ void __launch_bounds__(128) phnms_gather_kernel(const float *__restri
             if (lane == 0) out_index[(size_t)t * K + k] = 0;
         }
     }
+}
+
+// ---- get_lanes in ONE launch -----------------------------------------------------------------------
+// get_lanes uses only `keep[:num_to_keep]` of the op's three results (`keep, num_to_keep, _ = nms(...)`, Router4OL.py:460-465):
+// parent_object_index -- the part of the op that touches every proposal -- is never looked at.  What get_lanes needs is exactly
+// what the select step computes: the greedy scan over the proposals in rank order until top_k lanes are kept.  So for a clip the
+// whole of get_lanes' tensor work is one kernel, one warp per frame, reading the raw head output `pred` directly:
+//   * score = softmax(logits)[1] and the confidence filter while the rank keys are built (the filtered priors simply get no
+//     key; compaction keeps the prior order, so ordering by (key, prior index) IS the order of the compacted frame -- and when
+//     <= 32 priors survive, ATen's unstable bitonic network is replayed on the compacted scores, as torch's sort would);
+//   * the column drop and the pixel / strip scalings are applied to the few candidate rows when they are fetched -- the
+//     compacted, rescaled copy of the frame that the unfused pipeline writes to HBM and reads back never exists;
+//   * draws continue until top_k lanes are kept or the frame is exhausted (no cap: at most A priors), so there is no resume pass;
+//   * predictions[keep] with the length column(s) rounded is written straight from `pred`.
+// Same arithmetic as phnms_prepare_kernel / phnms_select_kernel / phnms_gather_kernel, bit for bit (tests/test_get_lanes_gpu.py).
+struct GetLanesFusedParams {
+    const float *pred;
+    long long T;
+    int A, hdr, n_off, top_k, sort_model;
+    float conf_thr, img_w_m1, n_strips, thr;
+    float *out_rows;
+    long long *out_num;
+    long long *out_index;
+    unsigned char *keep_inds;
+};
+
+__host__ __device__ inline int get_lanes_warp_words(int A, int n_off, int top_k) {
+    const int P4 = (5 + n_off + 3) & ~3, G = (A + 31) / 32;
+    const int w = top_k * (8 + P4) + kSelBatch * (P4 | 1) + 2 * kSelBatch + kSelBatch + 32 * (G | 1) + G + 8 + 64;
+    return (w + 3) & ~3;
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) phnms_get_lanes_fused_kernel(const GetLanesFusedParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_gl[];
+    __shared__ float bit_key[kSelWarps][32];
+    __shared__ int bit_val[kSelWarps][32];
+    __shared__ int bit_ok[kSelWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long t = (long long)blockIdx.x * nw + warp;
+    if (t >= gp.T) return;
+    const int A = gp.A, n_off = gp.n_off, hdr = gp.hdr, C = hdr + n_off, P = 5 + n_off, P4 = (P + 3) & ~3, slot_words = 8 + P4, bp = P4 | 1;
+    const int top_k = gp.top_k, G = (A + 31) / 32, pitch = G | 1;
+    uint32_t *slots = reinterpret_cast<uint32_t *>(smem_gl) + (size_t)warp * get_lanes_warp_words(A, n_off, top_k);
+    float *brow = reinterpret_cast<float *>(slots + top_k * slot_words);
+    int *bse = reinterpret_cast<int *>(brow + kSelBatch * bp);
+    uint32_t *adj = reinterpret_cast<uint32_t *>(bse + 2 * kSelBatch);
+    uint32_t *kb = adj + kSelBatch;                    // [32][pitch] rank keys
+    uint32_t *vm = kb + 32 * pitch;                    // [G] survivors of priors 32 q .. 32 q + 31
+    int *kept_idx = reinterpret_cast<int *>(vm + G);   // [8] prior index of the k-th kept lane
+    float *cs = reinterpret_cast<float *>(kept_idx + 8);   // [32] scores of the first 32 survivors, in prior order
+    int *ca = reinterpret_cast<int *>(cs + 32);            // [32] their prior indices
+    const float *frame = gp.pred + (size_t)t * A * C;
+    const bool nan_first = gp.sort_model == 1;
+
+    // ---- scores, the confidence filter, rank keys -----------------------------------------------------------------------------
+    u64 gmin = kNone64;
+    int n = 0;
+    for (int q = 0; q < G; ++q) {
+        const int a = lane + 32 * q;
+        bool keepf = false;
+        float score = 0.0f;
+        if (a < A) {
+            const float e0 = frame[(size_t)a * C], e1 = frame[(size_t)a * C + 1];
+            const float mx = (e1 < e0) ? e0 : e1;
+            const float x0 = expf(__fsub_rn(e0, mx)), x1 = expf(__fsub_rn(e1, mx));
+            score = __fdiv_rn(x1, __fadd_rn(x1, x0));
+            keepf = score >= gp.conf_thr;
+            gp.keep_inds[(size_t)t * A + a] = keepf ? 1 : 0;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keepf);
+        uint32_t k = 0xffffffffu;
+        if (keepf) {
+            k = key_desc(score, nan_first);
+            gmin = min(gmin, ((u64)k << 32) | (uint32_t)a);
+            const int pos = n + __popc(bal & ((1u << lane) - 1u));     // position in the compacted frame
+            if (pos < 32) {
+                cs[pos] = score;
+                ca[pos] = a;
+            }
+        }
+        kb[lane * pitch + q] = k;
+        if (lane == 0) vm[q] = bal;
+        n += __popc(bal);
+    }
+    __syncwarp();
+    const bool bitonic = gp.sort_model == 0 && n <= 32 && n >= 2;
+    u64 sorted = kNone64;
+    if (bitonic) {          // ATen bitonicSortKVInPlace<block_dim_x = 16> on the compacted scores (see topm.cuh)
+        float *bk = bit_key[warp];
+        int *bv = bit_val[warp], *bo = bit_ok[warp];
+        bo[lane] = lane < n;
+        bk[lane] = lane < n ? cs[lane] : 0.0f;
+        bv[lane] = lane < n ? lane : 0;
+        __syncwarp();
+        for (unsigned size = 2; size <= 32; size *= 2) {
+            const bool flag = (size != 32) && ((lane & (size / 2)) != 0);
+            for (unsigned stride = size / 2; stride > 0; stride /= 2) {
+                if (lane < 16) {
+                    const unsigned pa = 2 * lane - (lane & (stride - 1)), pb = pa + stride;
+                    const float ka = bk[pa], kbv = bk[pb];
+                    const int oa = bo[pa], ob = bo[pb];
+                    const bool sw = (gt_nan(ka, kbv) && oa) || !ob;
+                    if (sw == flag) {
+                        const int va = bv[pa], vb = bv[pb];
+                        bk[pa] = kbv; bk[pb] = ka;
+                        bv[pa] = vb; bv[pb] = va;
+                        bo[pa] = ob; bo[pb] = oa;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane < n) sorted = ((u64)(uint32_t)lane << 32) | (uint32_t)ca[bv[lane]];   // rank = sorted position, index = the prior
+    }
+
+    // ---- the greedy scan over the proposals in rank order, batch by batch ----------------------------------------------------------
+    int nk = 0, drawn = 0;
+    while (n > 0) {
+        u64 myc = kNone64;
+        int nb = 0;
+        if (bitonic) {
+            nb = min(kSelBatch, n - drawn);
+            const u64 v = __shfl_sync(0xffffffffu, sorted, (drawn + lane) & 31);
+            if (lane < nb) myc = v;
+        } else {
+            nb = select_draw_batch(gmin, kb, pitch, G, lane, myc, [&](int i, int q) { return ((vm[q] >> (i & 31)) & 1u) != 0u; });
+        }
+        if (nb == 0) break;
+        {   // candidate rows straight from `pred`: theta (and the invalid-length column) dropped, start_x / x in pixels, length in strips
+            float rv[kSelBatch][3];
+#pragma unroll
+            for (int j = 0; j < kSelBatch; ++j) {
+                const u64 kj = __shfl_sync(0xffffffffu, myc, j);
+                const float *row = frame + (size_t)(j < nb ? (uint32_t)kj : 0u) * C;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int i = lane + 32 * u;
+                    float v = 0.0f;
+                    if (j < nb && i < P) {
+                        if (i < 3) v = row[i];
+                        else if (i == 3) v = __fmul_rn(row[3], gp.img_w_m1);
+                        else if (i == 4) v = __fmul_rn(row[5], gp.n_strips);
+                        else v = __fmul_rn(row[hdr + (i - 5)], gp.img_w_m1);
+                    }
+                    rv[j][u] = v;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kSelBatch; ++j)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int i = lane + 32 * u;
+                    if (j < nb && i < P4) brow[j * bp + i] = rv[j][u];
+                }
+        }
+        __syncwarp();
+        nk = select_scan_batch(nb, myc, nk, top_k, n_off, gp.thr, slots, brow, bse, adj, lane, [&](int k, u64 Ka) {
+            if (lane == 0) kept_idx[k] = (int)(uint32_t)Ka;
+        });
+        drawn += nb;
+        if (nk == top_k || drawn >= n) break;
+    }
+    __syncwarp();
+
+    // ---- predictions[keep], the length column(s) rounded (Router4OL.py:465-470) ------------------------------------------------------
+    for (int k = 0; k < top_k; ++k) {
+        float *dst = gp.out_rows + ((size_t)t * top_k + k) * C;
+        if (k < nk) {
+            const int a = kept_idx[k];
+            const float *row = frame + (size_t)a * C;
+            for (int i = lane; i < C; i += 32) dst[i] = (i >= 5 && i < hdr) ? rintf(__fmul_rn(row[i], gp.n_strips)) : row[i];
+            if (lane == 0) gp.out_index[(size_t)t * top_k + k] = a;
+        } else {
+            for (int i = lane; i < C; i += 32) dst[i] = 0.0f;
+            if (lane == 0) gp.out_index[(size_t)t * top_k + k] = 0;
+        }
+    }
+    if (lane == 0) gp.out_num[t] = (long long)nk;
 }
 
 // ---- the training-side line IoU -----------------------------------------------------------

@@ -79,7 +79,7 @@ int ensure_max_smem(const void *kern, int smem_optin) {
 
 // experiment knobs of debug sessions, read once at load (never on the call path)
 struct EnvKnobs {
-    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, debug, skip;
+    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, debug, skip, small_batch;
     EnvKnobs() {
         auto geti = [](const char *n) { const char *v = getenv(n); return v ? atoi(v) : 0; };
         topm_count = geti("PHNMS_TOPM_COUNT");
@@ -90,6 +90,7 @@ struct EnvKnobs {
         stream_cpt = geti("PHNMS_STREAM_CPT");
         no_stream = getenv("PHNMS_NO_STREAM") != nullptr;
         debug = getenv("PHNMS_DEBUG") != nullptr;
+        small_batch = getenv("PHNMS_SMALL_BATCH") ? geti("PHNMS_SMALL_BATCH") : -1;
         skip = geti("PHNMS_SKIP");   // timing experiments only (results are wrong): 1 = no select, 2 = no stream, 4 = no resume
     }
 };
@@ -113,6 +114,8 @@ size_t tiled_workspace(int64_t F, int64_t N) {
     // order (i64) + radix ping-pong (4 x u32) + bitmask
     return (size_t)F * N * 8 + (size_t)F * N * 16 + (size_t)F * N * cb * 8 + 256;
 }
+
+constexpr long long kSmallBatchProposals = 2048;   // F * N at or below this: single-launch path (see make_plan)
 
 // Launch shape of the streaming kernel (stream.cuh): warps per CTA, how frames are cut into units when there are fewer
 // frames than SMs, the kept-block ring, the grid (one persistent CTA per SM).
@@ -202,8 +205,12 @@ int make_plan(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning
         // The streaming path: the default when nothing asks for the cluster kernels.  Its resume pass IS the register-resident
         // cluster kernel, so it needs that plan to exist (N <= 8192).
         const bool k_ok = top_k < 0 || (top_k >= 1 && top_k <= kStreamMaxK);
+        // A call with only a handful of proposals (PHNet's own call: ONE frame of <= 240) is launch-latency bound: it takes
+        // the register-resident cluster kernel with in-kernel selection -- one launch instead of three.
+        const long long small_limit = g_env.small_batch >= 0 ? g_env.small_batch : kSmallBatchProposals;
+        const bool small = (long long)F * N <= small_limit && t.variant == 0;
         const bool want_stream = t.variant == PHNMS_FUSED_STREAM ||
-                                 (t.variant == 0 && !t.cluster && !t.threads && !t.schedule && !g_env.no_stream);
+                                 (t.variant == 0 && !t.cluster && !t.threads && !t.schedule && !g_env.no_stream && !small);
         if (t.variant == PHNMS_FUSED_STREAM && (!reg_ok || !k_ok || t.cluster || t.threads || t.schedule)) return PHNMS_ERR_TUNING;
         if (reg_ok) {
             const int max_cpt = (n_off == 36) ? 2 : 1;
@@ -259,7 +266,7 @@ int make_plan(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning
                 pl->rows_per_cta = rpc;
                 pl->smem_bytes = L.total;
                 pl->grid = (int)(clusters * csize);
-                pl->launches = 2;  // phnms_topm_kernel + phnms_freg_kernel
+                pl->launches = small ? 1 : 2;  // (phnms_topm_kernel +) phnms_freg_kernel
                 // claim counter + per frame: candidate block (capacity) of the cluster kernel, which also covers the kept-lane
                 // block of the streaming path (kStreamMaxK slots), + resume flag and list entry
                 pl->workspace_bytes = 1024 + (size_t)F * kTopM * (kHdr + 4 * ((P + 3) & ~3)) + 2 * (((size_t)F * 4 + 255) & ~(size_t)255);
@@ -812,7 +819,11 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
             int topm_count = (top_k > 0 && top_k <= 4) ? (N > 384 ? 12 : 8) : kTopM;
             if (g_env.topm_count >= 2 && g_env.topm_count <= kTopM) topm_count = g_env.topm_count;   // experiment knob
             fp.topm_count = topm_count;
-            {
+            const bool single_launch = pl.launches == 1 || g_env.no_topm;   // small calls: in-kernel selection, static schedule
+            if (single_launch) {
+                fp.claim_ctr = nullptr;   // (the claim counter is zeroed by the top-M kernel, which does not run)
+                fp.topm_count = 0;
+            } else {
                 int warps = kTopmWarps;
                 while (warps > 1 && topm_smem_bytes((int)N, warps) > 160 * 1024) warps >>= 1;
                 const size_t sm = topm_smem_bytes((int)N, warps);
@@ -826,7 +837,7 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
-            fp.topm = g_env.no_topm ? nullptr : topm;   // debugging aid: force in-kernel candidate selection
+            fp.topm = single_launch ? nullptr : topm;
             const FregLayout RL = freg_layout(pl.rows_per_cta, 5 + n_off, pl.cluster);
 #define PHNMS_LAUNCH_FREG(TR, DY)                                                                              \
     do {                                                                                                       \
@@ -881,6 +892,12 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
 // ---- get_lanes for a clip: prepare -> lane NMS -> gather -----------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// get_lanes as ONE launch (frontend.cuh): the offset counts PHNet ships, at most 1024 priors, top_k within the select step's range
+static bool get_lanes_fused_ok(int64_t A, int n_off, int64_t top_k, const phnms_tuning *tuning) {
+    if (tuning && (tuning->path || tuning->variant || tuning->cluster || tuning->threads)) return false;   // an explicit device path
+    return (n_off == 36 || n_off == 72) && A <= 1024 && (top_k < 0 || (top_k >= 1 && top_k <= kStreamMaxK));
+}
+
 size_t phnms_get_lanes_workspace_bytes(int64_t T, int64_t A, int n_off, const phnms_tuning *tuning) {
     if (T < 0 || A < 0 || check_shape(T, A, n_off) != PHNMS_OK) return 0;
     const size_t P = 5 + (size_t)n_off;
@@ -897,8 +914,25 @@ int phnms_get_lanes_f32(const float *pred, int64_t T, int64_t A, int n_off, int 
     if ((hdr != 6 && hdr != 7) || top_k < 1 || top_k > A) return PHNMS_ERR_BAD_ARG;
     if (T == 0 || A == 0) return PHNMS_OK;
     if (!pred || !out_rows || !out_num || !out_index || !keep_inds) return PHNMS_ERR_BAD_ARG;
-    if (!ws || ws_bytes < phnms_get_lanes_workspace_bytes(T, A, n_off, tuning)) return PHNMS_ERR_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (get_lanes_fused_ok(A, n_off, top_k, tuning) && !g_env.no_stream) {   // one launch, no workspace
+        DeviceInfo dev;
+        rc = device_info(&dev);
+        if (rc != 0) return rc;
+        if (dev.cc_major != 10) return PHNMS_ERR_DEVICE;
+        GetLanesFusedParams gp;
+        gp.pred = pred; gp.T = T; gp.A = (int)A; gp.hdr = hdr; gp.n_off = n_off; gp.top_k = (int)top_k; gp.sort_model = sort_model;
+        gp.conf_thr = conf_threshold; gp.img_w_m1 = img_w - 1.0f; gp.n_strips = (float)(n_off - 1); gp.thr = nms_thres;
+        gp.out_rows = out_rows; gp.out_num = reinterpret_cast<long long *>(out_num);
+        gp.out_index = reinterpret_cast<long long *>(out_index); gp.keep_inds = keep_inds;
+        const int warps = kSelWarps;
+        const size_t sm = (size_t)warps * get_lanes_warp_words((int)A, n_off, (int)top_k) * 4;
+        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_get_lanes_fused_kernel), dev.smem_optin);
+        if (rc) return rc;
+        phnms_get_lanes_fused_kernel<<<(unsigned)((T + warps - 1) / warps), warps * 32, sm, stream>>>(gp);
+        return (int)cudaGetLastError();
+    }
+    if (!ws || ws_bytes < phnms_get_lanes_workspace_bytes(T, A, n_off, tuning)) return PHNMS_ERR_WORKSPACE;
     const size_t P = 5 + (size_t)n_off;
     unsigned char *b = reinterpret_cast<unsigned char *>(align256((size_t)ws));
     float *cprops = reinterpret_cast<float *>(b);            b += align256((size_t)T * A * P * 4);

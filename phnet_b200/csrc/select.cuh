@@ -78,6 +78,94 @@ __device__ __forceinline__ void batch_pair(int lane, int &a, int &b) {
     b = (int)(((lane < 16 ? B0 : B1) >> sh) & 15ull);
 }
 
+// ---- the two steps of a batch, shared by phnms_select_kernel and the fused get_lanes kernel (frontend.cuh) -------------------
+// Draw: the next (up to) kSelBatch proposals in rank order.  Lane l owns "group l" = proposals l, l + 32, ... and keeps the
+// group's smallest not-yet-drawn rank key in `gmin`; per pick one warp arg-min over the 32 group minima, then the warp
+// rescans the winning group (one key per lane) for its next minimum.  `valid(i, q)`: proposal i = g + 32 q exists.
+template <typename ValidFn>
+__device__ __forceinline__ int select_draw_batch(u64 &gmin, const uint32_t *kb, int pitch, int G, int lane, u64 &myc, ValidFn valid) {
+    int nb = 0;
+    myc = kNone64;
+    for (int j = 0; j < kSelBatch; ++j) {
+        const u64 best = warp_min_u64(gmin);
+        if (best == kNone64) break;
+        if (lane == j) myc = best;
+        ++nb;
+        const int g = (int)((uint32_t)best & 31u);       // the group (== lane) that owned the pick
+        u64 cand = kNone64;
+        for (int q = lane; q < G; q += 32) {              // rescan group g: proposal g + 32 q
+            const int i = g + 32 * q;
+            const u64 K = ((u64)kb[g * pitch + q] << 32) | (uint32_t)i;
+            if (valid(i, q) && K > best) cand = min(cand, K);
+        }
+        cand = warp_min_u64(cand);
+        if (lane == g) gmin = cand;
+    }
+    return nb;
+}
+
+// Scan: candidates j < nb (rank key of candidate j in lane j's `myc`, rows in brow) against the lanes kept so far (the mask
+// rows nms_collect would OR into remv, nms_kernel.cu:116-122), then the survivors against each other (strict upper triangle
+// in rank order, :85-87) and the greedy scan over the batch (:111-136).  Newly kept lanes are appended to `slots` (header +
+// row, the layout the streaming kernel reads); on_keep(k, Ka) is called by every lane for the k-th kept lane.  Returns nk.
+template <typename OnKeep>
+__device__ __forceinline__ int select_scan_batch(int nb, u64 myc, int nk, int top_k, int n_off, float thr, uint32_t *slots,
+                                                 float *brow, int *bse, uint32_t *adj, int lane, OnKeep on_keep) {
+    const int P4 = (5 + n_off + 3) & ~3, slot_words = 8 + P4, bp = P4 | 1;
+    if (lane < nb) {
+        const int st = lane_start(brow[lane * bp + 2], n_off);       // nms_kernel.cu:29-30
+        bse[2 * lane] = st;
+        bse[2 * lane + 1] = lane_end(brow[lane * bp + 4], st, n_off); // :32-34
+    }
+    if (lane < kSelBatch) adj[lane] = 0u;
+    __syncwarp();
+    uint32_t supp = 0u;
+    const int tot = nk * nb;
+    for (int b0 = 0; b0 < tot; b0 += 32) {
+        const int pr = b0 + lane;
+        uint32_t bit = 0u;
+        if (pr < tot) {
+            const int i = pr / nb, j = pr - i * nb;
+            const uint32_t *sl = slots + i * slot_words;
+            if (pair_hit_scalar(reinterpret_cast<const float *>(sl + 8), brow + j * bp, (int)sl[2], (int)sl[3], bse[2 * j],
+                                bse[2 * j + 1], thr))
+                bit = 1u << j;
+        }
+        supp |= __reduce_or_sync(0xffffffffu, bit);
+    }
+    const uint32_t surv = ~supp & ((1u << nb) - 1u);
+    const int s = __popc(surv), need = top_k - nk;
+    if (s >= 2 && need >= 2) {
+        int a, b;
+        batch_pair(lane, a, b);
+        if (lane < 28 && ((surv >> a) & (surv >> b) & 1u)) {
+            if (pair_hit_scalar(brow + a * bp, brow + b * bp, bse[2 * a], bse[2 * a + 1], bse[2 * b], bse[2 * b + 1], thr))
+                atomicOr(&adj[a], 1u << b);
+        }
+        __syncwarp();
+    }
+    uint32_t alive = surv;
+    while (alive && nk < top_k) {
+        const int a = __ffs(alive) - 1;
+        alive &= ~(1u << a);
+        alive &= ~adj[a];
+        const u64 Ka = __shfl_sync(0xffffffffu, myc, a);
+        uint32_t *sl = slots + nk * slot_words;
+        for (int i = lane; i < P4; i += 32) sl[8 + i] = __float_as_uint(brow[a * bp + i]);
+        if (lane == 0) {
+            const int st = bse[2 * a], en = bse[2 * a + 1];
+            uint32_t m[3];
+            range_mask<3>(st, en, m);
+            sl[0] = (uint32_t)(Ka >> 32); sl[1] = (uint32_t)Ka; sl[2] = (uint32_t)st; sl[3] = (uint32_t)en;
+            sl[4] = m[0]; sl[5] = m[1]; sl[6] = m[2]; sl[7] = 0u;
+        }
+        on_keep(nk, Ka);
+        ++nk;
+    }
+    __syncwarp();
+    return nk;
+}
+
 __global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_select_kernel(const SelectParams sp) {
     extern __shared__ __align__(16) unsigned char smem_sel[];
     __shared__ float bit_key[kSelWarps][32];
@@ -182,21 +270,7 @@ __global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_selec
             const u64 v = __shfl_sync(0xffffffffu, sorted, (drawn + lane) & 31);
             if (lane < nb) myc = v;
         } else {
-            for (int j = 0; j < kSelBatch; ++j) {
-                const u64 best = warp_min_u64(gmin);
-                if (best == kNone64) break;
-                if (lane == j) myc = best;
-                ++nb;
-                const int g = (int)((uint32_t)best & 31u);       // the group (== lane) that owned the pick
-                u64 cand = kNone64;
-                for (int q = lane; q < G; q += 32) {              // rescan group g: proposal g + 32 q
-                    const int i = g + 32 * q;
-                    const u64 K = ((u64)kb[g * pitch + q] << 32) | (uint32_t)i;
-                    if (i < n && K > best) cand = min(cand, K);
-                }
-                cand = warp_min_u64(cand);
-                if (lane == g) gmin = cand;
-            }
+            nb = select_draw_batch(gmin, kb, pitch, G, lane, myc, [&](int i, int) { return i < n; });
         }
         if (nb == 0) break;
         // ---- their rows: coalesced loads, all issued before the first store ---------------------------------------
@@ -221,59 +295,9 @@ __global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_selec
                 }
         }
         __syncwarp();
-        if (lane < nb) {
-            const int st = lane_start(brow[lane * bp + 2], n_off);       // nms_kernel.cu:29-30
-            bse[2 * lane] = st;
-            bse[2 * lane + 1] = lane_end(brow[lane * bp + 4], st, n_off); // :32-34
-        }
-        if (lane < kSelBatch) adj[lane] = 0u;
-        __syncwarp();
-        // ---- candidates against the lanes kept so far (the mask rows nms_collect would OR into remv, :116-122) ------
-        uint32_t supp = 0u;
-        const int tot = nk * nb;
-        for (int b0 = 0; b0 < tot; b0 += 32) {
-            const int pr = b0 + lane;
-            uint32_t bit = 0u;
-            if (pr < tot) {
-                const int i = pr / nb, j = pr - i * nb;
-                const uint32_t *sl = slots + i * slot_words;
-                if (pair_hit_scalar(reinterpret_cast<const float *>(sl + 8), brow + j * bp, (int)sl[2], (int)sl[3], bse[2 * j],
-                                    bse[2 * j + 1], sp.thr))
-                    bit = 1u << j;
-            }
-            supp |= __reduce_or_sync(0xffffffffu, bit);
-        }
-        const uint32_t surv = ~supp & ((1u << nb) - 1u);
-        // ---- survivors against each other (strict upper triangle in rank order, :85-87), then the scan over the batch ------
-        const int s = __popc(surv), need = top_k - nk;
-        if (s >= 2 && need >= 2) {
-            int a, b;
-            batch_pair(lane, a, b);
-            if (lane < 28 && ((surv >> a) & (surv >> b) & 1u)) {
-                if (pair_hit_scalar(brow + a * bp, brow + b * bp, bse[2 * a], bse[2 * a + 1], bse[2 * b], bse[2 * b + 1], sp.thr))
-                    atomicOr(&adj[a], 1u << b);
-            }
-            __syncwarp();
-        }
-        uint32_t alive = surv;
-        while (alive && nk < top_k) {
-            const int a = __ffs(alive) - 1;
-            alive &= ~(1u << a);
-            alive &= ~adj[a];
-            const u64 Ka = __shfl_sync(0xffffffffu, myc, a);
-            uint32_t *sl = slots + nk * slot_words;
-            for (int i = lane; i < P4; i += 32) sl[8 + i] = __float_as_uint(brow[a * bp + i]);
-            if (lane == 0) {
-                const int st = bse[2 * a], en = bse[2 * a + 1];
-                uint32_t m[3];
-                range_mask<3>(st, en, m);
-                sl[0] = (uint32_t)(Ka >> 32); sl[1] = (uint32_t)Ka; sl[2] = (uint32_t)st; sl[3] = (uint32_t)en;
-                sl[4] = m[0]; sl[5] = m[1]; sl[6] = m[2]; sl[7] = 0u;
-                sp.keep[(size_t)f * N + nk] = (long long)(uint32_t)Ka;   // :118
-            }
-            ++nk;
-        }
-        __syncwarp();
+        nk = select_scan_batch(nb, myc, nk, top_k, n_off, sp.thr, slots, brow, bse, adj, lane, [&](int k, u64 Ka) {
+            if (lane == 0) sp.keep[(size_t)f * N + k] = (long long)(uint32_t)Ka;   // :118
+        });
         drawn += nb;
         if (nk == top_k || drawn >= n) break;   // :133 / every proposal of the frame was drawn
         if (drawn >= sp.cap) {

@@ -61,6 +61,13 @@ def _check_inputs(boxes: torch.Tensor, scores: torch.Tensor, batched: bool):
     return boxes, scores
 
 
+def _as_top_k(top_k) -> int:
+    top_k = int(top_k)
+    if top_k < 0:
+        raise TypeError("top_k must be non-negative (unsigned long in the reference, nms.cpp:48)")
+    return top_k
+
+
 _ws_bytes_cache: dict = {}     # (F, N, n_off, tuning key) -> workspace bytes (a pure function of the shape)
 _ws_cache: dict = {}           # (device index, stream handle) -> reusable workspace tensor for small calls
 
@@ -142,6 +149,11 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model
     boxes  [N, 5+n_off] fp32 CUDA contiguous; scores [N]; overlap: pixel threshold; top_k: stop after this many lanes.
     Returns [keep[N] int64, num_to_keep[] int64, parent_object_index[N] int64] on the same device.
     """
+    if tuning is None and sort_model == _capi.SORT_TORCH_CUDA and type(boxes) is torch.Tensor and type(scores) is torch.Tensor \
+            and boxes.dtype == torch.float32 and scores.dtype == torch.float32 and scores.is_contiguous() and boxes.dim() == 2:
+        sh = _capi.shim()
+        if sh is not None:       # the reference's own native signature (nms.cpp:44-48); same checks, same C ABI call
+            return sh.nms_forward(boxes, scores, float(overlap), _as_top_k(top_k))
     boxes, scores = _check_inputs(boxes, scores, batched=False)
     N, P = boxes.shape
     out = torch.empty(2 * N + 1, dtype=torch.int64, device=boxes.device)   # one allocation, three views

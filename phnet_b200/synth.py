@@ -78,6 +78,26 @@ def make_frames_chunked(F: int, N: int, n_off: int, seed: int = 0, device="cuda"
     return props, scores
 
 
+def make_head_output(T: int, A: int, n_off: int, hdr: int, seed: int, groups: int = 8, logit_grid: float = 0.0):
+    """Raw detector-head output as `get_lanes` receives it (libs/models/Router4OL.py:437-447): [T, A, hdr + n_off] rows
+    (logit0, logit1, start_y, start_x, theta, length, [invalid_length when hdr == 7], x_0 ..), positions normalised to [0, 1].
+    logit_grid > 0 rounds the logits to that grid: the softmax scores are then well separated from each other and from any
+    threshold, so results do not depend on the last bit of a softmax implementation (CPU-generated fixtures)."""
+    props, _ = make_frames(T, A, n_off, seed=seed, groups=groups)
+    g = torch.Generator().manual_seed(seed + 1)
+    out = torch.empty((T, A, hdr + n_off), dtype=torch.float32)
+    logits = torch.randn((T, A, 2), generator=g) * 2.0
+    out[..., 0:2] = torch.round(logits / logit_grid) * logit_grid if logit_grid > 0 else logits
+    out[..., 2] = props[..., 2]
+    out[..., 3] = props[..., 3] / 767.0
+    out[..., 4] = torch.rand((T, A), generator=g)
+    out[..., 5] = props[..., 4] / (n_off - 1)
+    if hdr == 7:
+        out[..., 6] = torch.rand((T, A), generator=g) * 0.2
+    out[..., hdr:] = props[..., 5:] / 767.0
+    return out
+
+
 def edge_frame(n_off: int, seed: int = 0):
     """One small frame full of the awkward cases the reference code path contains (SURVEY.md section 8d edge suite):
     negative start_y (the `unsigned char` counter wrap), length in {-3, 0, 0.4, 1, 200}, NaN / Inf in x and in the

@@ -108,8 +108,10 @@ def test_plans():
         _capi.plan(4, 100, 50, _capi.tuning(variant=_capi.FUSED_STREAM))
     with pytest.raises(_capi.PhnmsError):
         _capi.plan(4, 1000, 72, _capi.tuning(variant=_capi.FUSED_STREAM), 0)
-    small = _capi.plan(2, 1000, 72)             # fewer frames than SMs: frames are cut into units so that every SM has work
-    assert small["variant"] == _capi.FUSED_STREAM and small["grid"] > 2
+    small = _capi.plan(8, 1000, 72)             # fewer frames than SMs: frames are cut into units so that every SM has work
+    assert small["variant"] == _capi.FUSED_STREAM and small["grid"] > 8
+    one = _capi.plan(1, 240, 72)                # PHNet's own call, one frame: launch-latency bound -> ONE launch (cluster kernel)
+    assert one["variant"] == _capi.FUSED_REG and one["launches"] == 1 and one["cluster"] == 1
     assert _capi.plan(1, 8192, 72)["path"] == _capi.PATH_FUSED          # the whole stress sweep stays on the fused path
     big = _capi.plan(1, 40000, 72)
     assert big["path"] == _capi.PATH_TILED and big["launches"] == 3 and big["workspace_bytes"] > 0
@@ -163,3 +165,18 @@ def test_header_is_plain_c(tmp_path):
     ver, rc, cluster, threads, ws = out.stdout.split()
     assert int(ver) == _capi.ABI_VERSION and int(rc) == 0 and int(cluster) == 1 and int(threads) == 512 and int(ws) > 0
     subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-x", "c++", os.path.join(inc, "phnms.h")], check=True)
+
+
+def test_pybind_shim_has_the_reference_native_surface():
+    """phnet_b200/csrc/nms_impl.so is a pybind11 module named like the reference's (`nms_impl`) exporting `nms_forward(boxes,
+    scores, thresh, top_k)` (libs/ops/csrc/nms.cpp:44-61); argument checks raise RuntimeError like CHECK_CUDA / CHECK_CONTIGUOUS."""
+    import torch
+    from phnet_b200 import build
+    build.build_shim()
+    sh = _capi.shim()
+    assert sh is not None and sh.__name__ == "nms_impl" and sh.abi_version() == _capi.ABI_VERSION
+    assert "nms_forward" in sh.nms_forward.__doc__ and "Tensor" in sh.nms_forward.__doc__
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sh.nms_forward(torch.zeros(8, 77), torch.zeros(8), 50.0, 4)
+    with pytest.raises(TypeError):
+        sh.nms_forward(torch.zeros(8, 77), torch.zeros(8), 50.0, -1)      # unsigned long top_k (nms.cpp:48)

@@ -9,20 +9,11 @@ from phnet_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def synth_head_output(T, A, n_off, hdr, seed, device):
-    """Raw head output: rows (logit0, logit1, start_y, start_x, theta, length, [invalid_len], x...) normalised like the model's."""
-    props, _ = synth.make_frames(T, A, n_off, seed=seed)
-    g = torch.Generator().manual_seed(seed + 1)
-    out = torch.empty((T, A, hdr + n_off), dtype=torch.float32)
-    out[..., 0:2] = torch.randn((T, A, 2), generator=g) * 2.0
-    out[..., 2] = props[..., 2]
-    out[..., 3] = props[..., 3] / 767.0
-    out[..., 4] = torch.rand((T, A), generator=g)
-    out[..., 5] = props[..., 4] / (n_off - 1)
-    if hdr == 7:
-        out[..., 6] = torch.rand((T, A), generator=g) * 0.2
-    out[..., hdr:] = props[..., 5:] / 767.0
-    return out.to(device)
+def synth_head_output(T, A, n_off, hdr, seed, device, groups=8):
+    return synth.make_head_output(T, A, n_off, hdr, seed, groups=groups).to(device)
+
+
+UNFUSED = dict(path=1)      # an explicit device path: prepare -> lane NMS -> gather (five launches) instead of the fused kernel
 
 
 def reference_get_lanes(predictions, conf_threshold, nms_thres, max_lanes, img_w, n_strips, hdr):
@@ -50,13 +41,18 @@ def reference_get_lanes(predictions, conf_threshold, nms_thres, max_lanes, img_w
     return predictions, keep_inds, keep
 
 
-@pytest.mark.parametrize("hdr,n_off,max_lanes,conf", [(6, 72, 4, 0.5), (6, 36, 4, 0.35), (7, 36, 8, 0.5), (6, 72, 4, 0.999), (6, 72, 4, 0.0)])
-def test_get_lanes_matches_reference_statements(cuda_device, hdr, n_off, max_lanes, conf):
+@pytest.mark.parametrize("tuning", [None, UNFUSED])
+@pytest.mark.parametrize("hdr,n_off,max_lanes,conf,groups", [(6, 72, 4, 0.5, 8), (6, 36, 4, 0.35, 3), (7, 36, 8, 0.5, 4), (6, 72, 4, 0.999, 8),
+                                                           (6, 72, 4, 0.0, 2), (6, 72, 8, 0.9, 2), (7, 36, 2, 0.2, 1)])
+def test_get_lanes_matches_reference_statements(cuda_device, hdr, n_off, max_lanes, conf, groups, tuning):
     T, A = 24, 240
-    out = synth_head_output(T, A, n_off, hdr, seed=hdr * 100 + n_off, device=cuda_device)
+    out = synth_head_output(T, A, n_off, hdr, seed=hdr * 100 + n_off, device=cuda_device, groups=groups)
     out[3, :, 0:2] = torch.tensor([5.0, -5.0], device=cuda_device)          # a frame where nothing passes the filter
     out[4, 7, 1] = float("nan")                                             # NaN logit: score NaN, filtered out
-    lanes, num, index, keep_inds = get_lanes(out, conf, 50, max_lanes, img_w=768)
+    out[5, :, 0:2] = torch.tensor([-8.0, 8.0], device=cuda_device)          # every score saturates: all ties
+    out[6, 30:, 0:2] = torch.tensor([5.0, -5.0], device=cuda_device)        # <= 32 survivors: torch's unstable small sort
+    out[6, :30, 0:2] = torch.round(out[6, :30, 0:2])                        # ... with ties among them
+    lanes, num, index, keep_inds = get_lanes(out, conf, 50, max_lanes, img_w=768, tuning=tuning)
     torch.cuda.synchronize()
     for t in range(T):
         want, want_mask, keep = reference_get_lanes(out[t].clone(), conf, 50, max_lanes, 768, n_off - 1, hdr)
@@ -68,6 +64,39 @@ def test_get_lanes_matches_reference_statements(cuda_device, hdr, n_off, max_lan
         if n:
             orig = torch.nonzero(want_mask).flatten()[keep]
             assert torch.equal(index[t, :n], orig), f"frame {t}: prior indices differ"
+
+
+def test_get_lanes_matches_the_reference_method_bodies(cuda_device):
+    """tests/golden/get_lanes_ref.npz: the reference's OWN `get_lanes` (Router4OL.py:437-479, RouterV4.py:394-442), cut out of its
+    files with `ast` and executed by tests/golden/make_get_lanes_fixtures.py; inputs are regenerated here from their seeds."""
+    import hashlib
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "get_lanes_ref.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    assert len(names) >= 5
+    for nm in names:
+        T, A, n_off, hdr, seed, groups, max_lanes = (int(v) for v in z[nm + "/args"])
+        conf = float(z[nm + "/conf"][0])
+        out = synth.make_head_output(T, A, n_off, hdr, seed=seed, groups=groups, logit_grid=0.25)
+        out[3, :, 0:2] = torch.tensor([5.0, -5.0])
+        assert hashlib.sha1(out.numpy().tobytes()).digest() == z[nm + "/output_sha1"].tobytes(), f"{nm}: regenerated input differs"
+        for tuning in (None, UNFUSED):
+            lanes, num, index, keep_inds = get_lanes(out.to(cuda_device), conf, 50, max_lanes, img_w=768, tuning=tuning)
+            torch.cuda.synchronize()
+            assert np.array_equal(num.cpu().numpy(), z[nm + "/num"]), f"{nm} {tuning}: lanes kept per frame differ"
+            assert np.array_equal(lanes.cpu().numpy(), z[nm + "/rows"]), f"{nm} {tuning}: kept rows differ from the reference's"
+            for t in range(T):
+                assert np.array_equal(keep_inds[t].cpu().numpy(), z[f"{nm}/keep_inds{t}"]), f"{nm} frame {t}: confidence mask differs"
+
+
+def test_get_lanes_fused_and_unfused_agree_on_a_long_clip(cuda_device):
+    for hdr, n_off, K, A in ((6, 72, 4, 240), (7, 36, 8, 240), (6, 36, 4, 1000), (6, 72, 8, 33)):
+        out = synth_head_output(700, A, n_off, hdr, seed=A + K, device=cuda_device, groups=3)
+        a = get_lanes(out, 0.4, 50, K)
+        b = get_lanes(out, 0.4, 50, K, tuning=UNFUSED)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), f"hdr={hdr} n_off={n_off} K={K} A={A}"
 
 
 def test_scores_are_bitwise_torch_softmax(cuda_device):
