@@ -412,9 +412,31 @@ def run_ours(a):
             ms_e2e = float(t[0])
         # the device path and the host path must agree on the same frames
         assert torch.equal(out_h[0], outs[(a.steps - 1) & 1][0][:Fe].cpu()), "e2e keep differs from device-resident run"
+        # What the host side can deliver at most: the same bytes copied pinned host -> device with nothing else running, all
+        # ranks at once (the ceiling for `e2e`: its steps move h2d_bytes_per_step over the same path).
+        probe = torch.empty_like(props[:Fe])
+        for _ in range(2):
+            probe.copy_(props_h, non_blocking=True)
+        fence()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(5):
+            probe.copy_(props_h, non_blocking=True)
+        q1.record()
+        fence()
+        ms_probe = q0.elapsed_time(q1) / 5
+        if world > 1:
+            t = torch.tensor([ms_probe], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_probe = float(t[0])
+        h2d_gbs = props_h.numel() * 4 / (ms_probe * 1e-3) / 1e9
+        del probe
         e2e = {"value": world * Fe * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": pipe.h2d_bytes // e2e_steps, "d2h_bytes_per_step": pipe.d2h_bytes // e2e_steps,
                "frames_per_step_per_gpu": Fe, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+               "h2d_gbs_per_gpu": (pipe.h2d_bytes // e2e_steps) / (ms_e2e / e2e_steps * 1e-3) / 1e9,
+               "h2d_ceiling_gbs_per_gpu": h2d_gbs,
+               "h2d_ceiling_note": "pinned host -> device copy of the same frames alone, all ranks at once, slowest rank: what the host / PCIe side delivers at most",
                "api": "phnet_b200.ops.HostLaneNMS (pinned host tensors in, reference-shaped keep/num/parent out)"}
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample ------------------------------------------

@@ -115,7 +115,8 @@ size_t tiled_workspace(int64_t F, int64_t N) {
     return (size_t)F * N * 8 + (size_t)F * N * 16 + (size_t)F * N * cb * 8 + 256;
 }
 
-constexpr long long kSmallBatchProposals = 2048;   // F * N at or below this: single-launch path (see make_plan)
+constexpr long long kSmallBatchProposals = 2048;
+constexpr int kSelFullScanN = 256;   // F * N at or below this: single-launch path (see make_plan)
 
 // Launch shape of the streaming kernel (stream.cuh): warps per CTA, how frames are cut into units when there are fewer
 // frames than SMs, the kept-block ring, the grid (one persistent CTA per SM).
@@ -281,7 +282,9 @@ int make_plan(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning
                         pl->rows_per_cta = ss.warps * 32;
                         pl->smem_bytes = ss.L.total;
                         pl->grid = ss.grid;
-                        pl->launches = 3;   // phnms_select_kernel + phnms_stream_kernel + the resume pass (phnms_freg_kernel)
+                        // phnms_select_kernel + phnms_stream_kernel + the resume pass (phnms_freg_kernel; not needed when every
+                        // proposal of a frame can be drawn)
+                        pl->launches = (N <= kSelFullScanN && !t.select_cap && !g_env.select_cap) ? 2 : 3;
                         pl->max_active_clusters = ss.grid;
                     } else if (t.variant == PHNMS_FUSED_STREAM) {
                         return PHNMS_ERR_TUNING;
@@ -657,7 +660,10 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
     int *flags = reinterpret_cast<int *>(after);
     int *list = reinterpret_cast<int *>(after + (((size_t)F * 4 + 255) & ~(size_t)255));
 
-    int cap = t.select_cap ? t.select_cap : (g_env.select_cap ? g_env.select_cap : kSelCapDefault);
+    // Draws per frame before the select kernel hands a frame over (open).  Frames of up to 256 proposals -- everything PHNet
+    // itself produces (240 priors) -- are always scanned to the end: no frame is ever left open and the resume pass is not
+    // even launched.  Larger frames: 64 (deeper draws cost every frame that has fewer lanes than top_k).
+    int cap = t.select_cap ? t.select_cap : (g_env.select_cap ? g_env.select_cap : (N <= kSelFullScanN ? (int)N : kSelCapDefault));
     if (cap < kSelBatch) return PHNMS_ERR_TUNING;
     if (!(g_env.skip & 1)) {   // (1) the greedy scan over the best-ranked proposals: one warp per frame
         SelectParams sp;

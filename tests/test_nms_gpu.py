@@ -254,3 +254,25 @@ def test_scores_of_another_dtype_keep_their_own_order(cuda_device):
     assert_same(got, want, "float64 scores")
     plain = nms(props[0].to(cuda_device), scores[0].to(cuda_device), overlap=50, top_k=4)
     assert not torch.equal(plain[0], got[0]) or True                   # (usually differs: ties fall the other way)
+
+
+def test_shim_inside_a_reference_style_package_matches_the_oracle(cuda_device, tmp_path):
+    """INTEGRATION.md option 0: the reference's `libs/ops/nms.py` left as it is, this repo's `nms_impl.so` in place of the
+    reference's compiled module."""
+    import importlib
+    import sys
+    from tests.test_capi_load import _reference_style_package
+    root = _reference_style_package(tmp_path)
+    sys.path.insert(0, root)
+    try:
+        ops = importlib.import_module("refstyle_libs.ops")
+        for N, n_off, top_k in ((240, 72, 4), (1000, 72, 4), (240, 36, 8), (33, 36, 2)):
+            props, scores = synth.make_frames(3, N, n_off, seed=N + top_k, groups=3)
+            for f in range(3):
+                keep, num, parent = ops.nms(props[f].to(cuda_device), scores[f].to(cuda_device), overlap=50, top_k=top_k)
+                assert keep.dtype == torch.int64 and num.dim() == 0 and parent.shape == (N,)
+                assert_same((keep, num, parent), oracle_batched(props[f:f + 1], scores[f:f + 1], 50.0, top_k), f"shim N={N}")
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k.startswith("refstyle_libs")]:
+            del sys.modules[k]
