@@ -58,6 +58,10 @@ extern "C" {
                                        TMA-fed, no cluster) evaluates every proposal against the kept lanes; frames the
                                        select kernel could not finish are redone by the PHNMS_FUSED_REG kernel          */
 
+#define PHNMS_FUSED_SMALL 4         /* calls of <= 2048 proposals in total with <= 512 per frame (PHNet's own call: one frame of
+                                       <= 240 priors): ONE launch, one CTA per frame, rows in registers, one greedy round per
+                                       kept lane, any top_k, no workspace                                               */
+
 /* how frames are handed to the persistent clusters of the register-resident kernel */
 #define PHNMS_SCHED_STATIC 1        /* cluster c takes frames c, c + n_clusters, ...: fastest when the GPU is not shared         */
 #define PHNMS_SCHED_DYNAMIC 2       /* clusters claim frames from a counter: no second wave when another kernel holds some SMs   */
@@ -67,7 +71,7 @@ typedef struct phnms_tuning {
     int cluster;         /* CTAs per frame for the fused path: 1,2,4,8,16            (0 = auto) */
     int threads;         /* threads per CTA for the fused path: multiple of 32, <=512 (0 = auto) */
     int max_clusters;    /* cap on resident clusters (persistent grid size)          (0 = auto) */
-    int variant;         /* fused path: PHNMS_FUSED_SMEM / _REG / _STREAM            (0 = auto) */
+    int variant;         /* fused path: PHNMS_FUSED_SMEM / _REG / _STREAM / _SMALL   (0 = auto) */
     int schedule;        /* register-resident kernel: PHNMS_SCHED_STATIC / _DYNAMIC   (0 = auto) */
     int stream_warps;    /* streaming kernel: warps per CTA, 1..16                   (0 = auto) */
     int select_cap;      /* select kernel: proposals drawn per frame before the frame is handed to the resume
@@ -84,7 +88,7 @@ typedef struct phnms_plan {
     int smem_bytes;      /* dynamic shared memory per CTA */
     int grid;            /* CTAs launched */
     int launches;        /* kernel launches one phnms_forward_f32 call makes */
-    int variant;         /* PHNMS_FUSED_SMEM / _REG / _STREAM (fused path), 0 otherwise */
+    int variant;         /* PHNMS_FUSED_SMEM / _REG / _STREAM / _SMALL (fused path), 0 otherwise */
     int cols_per_thread; /* proposals held per thread (register-resident variant) */
     int max_active_clusters; /* cudaOccupancyMaxActiveClusters for this launch (0 when no device was queried) */
     size_t workspace_bytes;

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("PHNMS_SO") or os.path.join(HERE, "csrc", "libphnms.so")   # PHNMS_SO: A/B testing of builds
 
 PATH_AUTO, PATH_FUSED, PATH_TILED = 0, 1, 2
-FUSED_SMEM, FUSED_REG, FUSED_STREAM = 1, 2, 3
+FUSED_SMEM, FUSED_REG, FUSED_STREAM, FUSED_SMALL = 1, 2, 3, 4
 SCHED_STATIC, SCHED_DYNAMIC = 1, 2
 SORT_TORCH_CUDA, SORT_STABLE, SORT_STABLE_RADIX = 0, 1, 2
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libphnms.so")
 SOURCES = ["phnms.cu"]
-HEADERS = ["common.cuh", "fused_nms.cuh", "fused_reg.cuh", "topm.cuh", "select.cuh", "stream.cuh", "tiled_nms.cuh", "frontend.cuh",
+HEADERS = ["common.cuh", "fused_nms.cuh", "fused_reg.cuh", "topm.cuh", "select.cuh", "stream.cuh", "small.cuh", "tiled_nms.cuh", "frontend.cuh",
            os.path.join("..", "..", "include", "phnms.h")]
 
 NVCC_FLAGS = [

@@ -18,6 +18,7 @@
 #include "select.cuh"
 #include "stream.cuh"
 #include "frontend.cuh"
+#include "small.cuh"
 
 using namespace phnms;
 
@@ -79,7 +80,7 @@ int ensure_max_smem(const void *kern, int smem_optin) {
 
 // experiment knobs of debug sessions, read once at load (never on the call path)
 struct EnvKnobs {
-    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, debug, skip, small_batch;
+    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, no_small, debug, skip, small_batch;
     EnvKnobs() {
         auto geti = [](const char *n) { const char *v = getenv(n); return v ? atoi(v) : 0; };
         topm_count = geti("PHNMS_TOPM_COUNT");
@@ -89,6 +90,7 @@ struct EnvKnobs {
         stream_warps = geti("PHNMS_STREAM_WARPS");
         stream_cpt = geti("PHNMS_STREAM_CPT");
         no_stream = getenv("PHNMS_NO_STREAM") != nullptr;
+        no_small = getenv("PHNMS_NO_SMALL") != nullptr;
         debug = getenv("PHNMS_DEBUG") != nullptr;
         small_batch = getenv("PHNMS_SMALL_BATCH") ? geti("PHNMS_SMALL_BATCH") : -1;
         skip = geti("PHNMS_SKIP");   // timing experiments only (results are wrong): 1 = no select, 2 = no stream, 4 = no resume
@@ -213,6 +215,21 @@ int make_plan(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning
         const bool want_stream = t.variant == PHNMS_FUSED_STREAM ||
                                  (t.variant == 0 && !t.cluster && !t.threads && !t.schedule && !g_env.no_stream && !small);
         if (t.variant == PHNMS_FUSED_STREAM && (!reg_ok || !k_ok || t.cluster || t.threads || t.schedule)) return PHNMS_ERR_TUNING;
+        // ... and when its frames have at most 512 proposals, the one-launch kernel of small.cuh: one CTA per frame, no workspace
+        const bool small_ok = reg_ok && N <= kSmallMaxN && !t.cluster && !t.threads && !t.schedule;
+        if (t.variant == PHNMS_FUSED_SMALL && !small_ok) return PHNMS_ERR_TUNING;
+        if (small_ok && (t.variant == PHNMS_FUSED_SMALL || (small && !g_env.no_small)) && F <= 0x7fffffff) {
+            const int warps = N > 32 ? (int)((N + 31) / 32) : 1;
+            pl->path = PHNMS_PATH_FUSED;
+            pl->variant = PHNMS_FUSED_SMALL;
+            pl->cluster = 1;
+            pl->threads = warps * 32;
+            pl->rows_per_cta = warps * 32;
+            pl->smem_bytes = small_layout(warps, P).total;
+            pl->grid = (int)(F > 0 ? F : 1);
+            pl->max_active_clusters = pl->grid;
+            return PHNMS_OK;
+        }
         if (reg_ok) {
             const int max_cpt = (n_off == 36) ? 2 : 1;
             // The smallest cluster whose CTAs can hold their share of the frame.  Threads: one (n_off 72) or two (n_off 36)
@@ -414,7 +431,7 @@ int fused_occupancy(const phnms_plan &pl, int n_off) {
 }
 
 void fit_grid_to_occupancy(phnms_plan *pl, int64_t F, int n_off, const phnms_tuning *tun) {
-    if (pl->path != PHNMS_PATH_FUSED || pl->variant == PHNMS_FUSED_STREAM) return;
+    if (pl->path != PHNMS_PATH_FUSED || pl->variant == PHNMS_FUSED_STREAM || pl->variant == PHNMS_FUSED_SMALL) return;
     const int occ = fused_occupancy(*pl, n_off);
     pl->max_active_clusters = occ;
     if (occ <= 0) return;
@@ -664,7 +681,10 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
     // itself produces (240 priors) -- are always scanned to the end: no frame is ever left open and the resume pass is not
     // even launched.  Larger frames: 64 (deeper draws cost every frame that has fewer lanes than top_k).
     int cap = t.select_cap ? t.select_cap : (g_env.select_cap ? g_env.select_cap : (N <= kSelFullScanN ? (int)N : kSelCapDefault));
-    if (cap < kSelBatch) return PHNMS_ERR_TUNING;
+    if (cap < kSelBatch) {
+        if (t.select_cap || g_env.select_cap) return PHNMS_ERR_TUNING;   // an explicit cap below one batch
+        cap = kSelBatch;   // frames of fewer than 8 proposals: one batch draws them all
+    }
     if (!(g_env.skip & 1)) {   // (1) the greedy scan over the best-ranked proposals: one warp per frame
         SelectParams sp;
         sp.props = props; sp.scores = scores; sp.n_valid = n_valid;
@@ -773,12 +793,30 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
     phnms_tuning traced;
     if (trace) {   // the phase trace belongs to the register-resident cluster kernel
         traced = tuning ? *tuning : phnms_tuning{};
-        if (traced.variant == 0 || traced.variant == PHNMS_FUSED_STREAM) traced.variant = PHNMS_FUSED_REG;
+        if (traced.variant == 0 || traced.variant == PHNMS_FUSED_STREAM || traced.variant == PHNMS_FUSED_SMALL) traced.variant = PHNMS_FUSED_REG;
         tuning = &traced;
     }
     rc = make_plan(F, N, n_off, top_k, tuning, &dev, &pl);
     if (rc != PHNMS_OK) return rc;
     if (F > 1) fit_grid_to_occupancy(&pl, F, n_off, tuning);
+    if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_SMALL && !trace) {   // one launch, one CTA per frame
+        SmallParams q;
+        q.props = props; q.scores = scores; q.n_valid = n_valid;
+        q.keep = reinterpret_cast<long long *>(keep);
+        q.num_keep = reinterpret_cast<long long *>(num_keep);
+        q.parent = reinterpret_cast<long long *>(parent);
+        q.F = F; q.top_k = top_k; q.N = (int)N; q.sort_model = sort_model; q.thr = thresh;
+        if (n_off == 72) {
+            rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<72>), dev.smem_optin);
+            if (rc) return fail_at("small smem attribute", rc);
+            phnms_small_kernel<72><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q);
+        } else {
+            rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<36>), dev.smem_optin);
+            if (rc) return fail_at("small smem attribute", rc);
+            phnms_small_kernel<36><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q);
+        }
+        return fail_at("small launch", (int)cudaGetLastError());
+    }
     if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_STREAM)
         return launch_stream(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
                              tuning, dev, pl, stream);

@@ -1,0 +1,213 @@
+// small.cuh -- the whole op for a SMALL call in one launch: one CTA per frame, every proposal of the frame in registers.
+//
+// PHNet calls the op once per frame (libs/models/Router4OL.py:460-465: `keep, num_to_keep, _ = nms(...)` on the <= 240 priors
+// that passed the confidence filter), so what matters there is the latency of one launch, not bandwidth.  This kernel is the
+// shortest dependent chain I could find for the reference's three steps (nms.cpp:51 sort, nms_kernel.cu:50-96 mask rows,
+// :99-143 collect) on one frame of <= 512 proposals:
+//
+//   1. every warp fetches its own 32 rows with ONE bulk copy (UBLKCP; <= 3 unaligned words at either end and the scores by
+//      4-byte cp.async) onto its own mbarrier -- no CTA-wide step -- and moves them to registers (one proposal per thread);
+//   2. greedy rounds, one per kept lane: CTA-wide arg-min of the rank keys of the proposals still alive (REDUX in the warp,
+//      one shared-memory hop across warps), the winner publishes its row in the slot format of the streaming path, all
+//      threads evaluate devIoU against it over their registers (stream_eval: the reference's sequential fp32 sum) and stamp
+//      `parent` -- exactly the rows of the mask nms_collect reads (:116-129), in the order it reads them;
+//   3. outputs once: keep[0..nk) as the rounds go, zero padding, parent, num_to_keep = min(top_k, nk) (:139-142).
+//
+// Two __syncthreads per round, everything double buffered; top_k = 0 (never stops, reports 0) simply runs until no proposal
+// is alive.  Frames of <= 32 proposals under the torch sort model are ordered by ATen's bitonic network (replayed, see
+// select.cuh).  Used by the planner for calls of at most 2048 proposals in total (phnms.cu, make_plan).
+#pragma once
+#include "common.cuh"
+#include "fused_reg.cuh"
+#include "stream.cuh"
+
+namespace phnms {
+
+constexpr int kSmallMaxN = 512;
+
+struct SmallParams {
+    const float *props;
+    const float *scores;
+    const int32_t *n_valid;
+    long long *keep;
+    long long *num_keep;
+    long long *parent;
+    long long F;
+    long long top_k;
+    int N, sort_model;
+    float thr;
+};
+
+struct SmallLayout {
+    int off_wmin, off_bit, off_pub, off_slots, slot_bytes, total;
+};
+
+// shared memory: [0,128) one mbarrier per warp | wmin[2][16] u64 | bitonic scratch | 2 published slots | per-warp staging
+__host__ __device__ inline SmallLayout small_layout(int warps, int P) {
+    SmallLayout L;
+    const int P4 = (P + 3) & ~3;
+    int o = 128;
+    L.off_wmin = o;
+    o += 2 * 16 * 8;
+    L.off_bit = o;
+    o += 384;
+    L.off_pub = o;
+    o += 2 * (kHdr + 4 * P4);
+    o = (o + 127) & ~127;
+    L.off_slots = o;
+    L.slot_bytes = 128 + ((16 + 32 * P * 4 + 16 + 127) & ~127);
+    o += warps * L.slot_bytes;
+    L.total = o;
+    return L;
+}
+
+template <int NOFF>
+__global__ void __launch_bounds__(kSmallMaxN, 1) phnms_small_kernel(const SmallParams sp) {
+    constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const long long f = blockIdx.x;
+    const SmallLayout L = small_layout(nwarps, P);
+    const uint32_t smem_s = smem_u32(smem);
+    const uint32_t bar = smem_s + 8u * warp;
+    const uint32_t slot_s = smem_s + (uint32_t)L.off_slots + (uint32_t)warp * (uint32_t)L.slot_bytes;
+    u64 *wmin = reinterpret_cast<u64 *>(smem + L.off_wmin);
+    const int N = sp.N;
+    int n = N;
+    if (sp.n_valid) n = max(0, min(sp.n_valid[f], N));
+
+    // ---- 1. this warp's rows -> its staging slot -> registers ------------------------------------------------------------------
+    const int r0 = warp * 32, nrows = max(0, min(n - r0, 32));
+    const float *src = sp.props + ((size_t)f * N + r0) * P;
+    const uintptr_t a0 = (uintptr_t)src;
+    if (nrows > 0) {
+        if (lane == 0) {
+            mbar_init(bar, 33);   // 1 expect_tx arrive + 32 cp.async arrives
+            fence_mbar_init();
+        }
+        __syncwarp();
+        // (the same request as phnms_stream_kernel's: rows keep their global address modulo 16, the aligned body is one bulk copy)
+        const uint32_t bytes = (uint32_t)nrows * (P * 4);
+        if (((a0 | bytes) & 15u) == 0u) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(slot_s + 128u, src, bytes, bar);
+            }
+        } else {
+            const uintptr_t b0 = (a0 + 15) & ~(uintptr_t)15, e0 = (a0 + bytes) & ~(uintptr_t)15;
+            const uint32_t D = slot_s + 128u + (uint32_t)(a0 & 15);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)(e0 - b0));
+                bulk_g2s(D + (uint32_t)(b0 - a0), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar);
+            }
+            const int hw = (int)((b0 - a0) >> 2), tw = (int)((a0 + bytes - e0) >> 2), t0 = (int)((e0 - a0) >> 2);
+            if (lane >= 1 && lane - 1 < hw) cp_async_4(D + 4u * (uint32_t)(lane - 1), src + (lane - 1));
+            if (lane >= 4 && lane - 4 < tw) cp_async_4(D + 4u * (uint32_t)(t0 + lane - 4), src + t0 + (lane - 4));
+        }
+        if (lane < nrows) cp_async_4(slot_s + 4u * (uint32_t)lane, sp.scores + (size_t)f * N + r0 + lane);
+        cp_async_mbar_arrive_noinc(bar);
+    }
+
+    float x[1][NOFF];
+    int st[1] = {0}, en[1] = {-1};
+    float score = 0.0f;
+    const bool real[1] = {lane < nrows};
+    const uint32_t row = slot_s + 128u + (uint32_t)(a0 & 15) + (uint32_t)(real[0] ? lane : 0) * (P * 4);
+    if (nrows > 0) {
+        mbar_wait(bar, 0u);
+#pragma unroll
+        for (int i = 0; i < NOFF; ++i) x[0][i] = __uint_as_float(lds_u32(row + 4u * (5 + i)));
+        st[0] = lane_start(__uint_as_float(lds_u32(row + 8u)), NOFF);            // nms_kernel.cu:29-30
+        en[0] = lane_end(__uint_as_float(lds_u32(row + 16u)), st[0], NOFF);      // :32-34
+        score = __uint_as_float(lds_u32(slot_s + 4u * (uint32_t)(real[0] ? lane : 0)));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NOFF; ++i) x[0][i] = 0.0f;
+    }
+    // rank key: ascending u64 (key << 32 | index) == the order of scores.sort(0, true) (nms.cpp:51)
+    uint32_t key = key_desc(real[0] ? score : 0.0f, sp.sort_model == 1);
+    if (sp.sort_model == 0 && n <= 32 && n >= 2 && warp == 0) {   // ATen bitonicSortKVInPlace (SortUtils.cuh:45-163): unstable
+        float *bit_key = reinterpret_cast<float *>(smem + L.off_bit);
+        int *bit_val = reinterpret_cast<int *>(bit_key + 32), *bit_ok = bit_val + 32;
+        bit_ok[lane] = lane < n;
+        bit_key[lane] = lane < n ? score : 0.0f;
+        bit_val[lane] = lane < n ? lane : 0;
+        __syncwarp();
+        for (unsigned size = 2; size <= 32; size *= 2) {
+            const bool flag = (size != 32) && ((lane & (size / 2)) != 0);
+            for (unsigned stride = size / 2; stride > 0; stride /= 2) {
+                if (lane < 16) {
+                    const unsigned pa = 2 * lane - (lane & (stride - 1)), pb = pa + stride;
+                    const float ka = bit_key[pa], kb = bit_key[pb];
+                    const int oa = bit_ok[pa], ob = bit_ok[pb];
+                    const bool sw = (gt_nan(ka, kb) && oa) || !ob;
+                    if (sw == flag) {
+                        const int va = bit_val[pa], vb = bit_val[pb];
+                        bit_key[pa] = kb; bit_key[pb] = ka;
+                        bit_val[pa] = vb; bit_val[pb] = va;
+                        bit_ok[pa] = ob;  bit_ok[pb] = oa;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        int mypos = 0;
+        for (int q = 0; q < 32; ++q)
+            if (bit_val[q] == lane && q < n) mypos = q;
+        key = (uint32_t)mypos;
+    }
+    const u64 myK[1] = {real[0] ? (((u64)key << 32) | (uint32_t)(r0 + lane)) : kNone64};
+    uint32_t mb[1][MW], par[1] = {0u};
+    range_mask<MW>(st[0], en[0], mb[0]);
+
+    // ---- 2. greedy rounds (nms_collect, :111-136) -------------------------------------------------------------------------------
+    bool alive = real[0];
+    long long nk = 0;
+    uint32_t parity = 0u;
+    while (n > 0) {
+        const u64 wm = warp_min_u64(alive ? myK[0] : kNone64);
+        if (lane == 0) wmin[parity * 16 + warp] = wm;
+        __syncthreads();
+        const u64 best = warp_min_u64(lane < nwarps ? wmin[parity * 16 + lane] : kNone64);
+        if (best == kNone64) break;   // nobody left (:116 never true again)
+        unsigned char *pub = smem + L.off_pub + parity * SLOT;
+        if (myK[0] == best) {         // the kept lane publishes {rank key, index, start, end, in-range masks} + its row
+            uint32_t *h = reinterpret_cast<uint32_t *>(pub);
+            uint32_t m3[3];
+            range_mask<3>(st[0], en[0], m3);
+            h[0] = (uint32_t)(best >> 32); h[1] = (uint32_t)best; h[2] = (uint32_t)st[0]; h[3] = (uint32_t)en[0];
+            h[4] = m3[0]; h[5] = m3[1]; h[6] = m3[2]; h[7] = 0u;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) h[8 + i] = lds_u32(row + 4u * i);
+#pragma unroll
+            for (int i = 0; i < NOFF; ++i) h[8 + 5 + i] = __float_as_uint(x[0][i]);
+#pragma unroll
+            for (int i = P; i < P4; ++i) h[8 + i] = 0u;
+            sp.keep[(size_t)f * N + nk] = (long long)(uint32_t)best;   // :118
+        }
+        __syncthreads();
+        const uint32_t pub_s = smem_s + (uint32_t)L.off_pub + parity * SLOT;
+        if (!stream_eval<NOFF, 1, 1>(pub_s, 1, real, myK, st, en, mb, x, sp.thr, par, (int)nk)) {
+            // a pair with a negative common start somewhere in the warp (header words / the wrapped unsigned-char counter, :38)
+            FusedParams fp;
+            fp.thr = sp.thr;
+            auto my_hdr = [&](int) { return sp.props + ((size_t)f * N + (uint32_t)(r0 + lane)) * P; };
+            const unsigned char *const h1[1] = {pub};
+            bool hit[1][1];
+            freg_eval<NOFF, 1, 1>(fp, f, h1, real, myK, st, en, mb, x, my_hdr, par, hit, nk);
+        }
+        if (par[0] == (uint32_t)(nk + 1)) alive = false;   // covered by this lane (:120-122), or the lane itself
+        ++nk;
+        if (nk == sp.top_k) break;    // :133
+        parity ^= 1u;
+    }
+
+    // ---- 3. outputs ------------------------------------------------------------------------------------------------------------------
+    if (tid < N) {
+        sp.parent[(size_t)f * N + tid] = (long long)par[0];
+        if (tid >= nk) sp.keep[(size_t)f * N + tid] = 0ll;   // :139-140
+    }
+    if (tid == 0) sp.num_keep[f] = sp.top_k < nk ? sp.top_k : nk;   // :142
+}
+
+}  // namespace phnms

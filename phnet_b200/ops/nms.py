@@ -142,6 +142,17 @@ def _launch_f64(boxes, scores, n_valid, F, N, n_off, overlap, top_k, keep, num, 
     _capi.check(rc)
 
 
+_Tensor, _f32 = torch.Tensor, torch.float32
+_shim_forward = None     # nms_impl.nms_forward once bound; False when the shim is not built
+
+
+def _bind_shim():
+    global _shim_forward
+    sh = _capi.shim()
+    _shim_forward = sh.nms_forward if sh is not None else False
+    return _shim_forward
+
+
 def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model: int = _capi.SORT_TORCH_CUDA,
         tuning=None):
     """Drop-in for `libs.ops.nms` (libs/ops/nms.py:32).
@@ -149,11 +160,16 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, overlap, top_k, *, sort_model
     boxes  [N, 5+n_off] fp32 CUDA contiguous; scores [N]; overlap: pixel threshold; top_k: stop after this many lanes.
     Returns [keep[N] int64, num_to_keep[] int64, parent_object_index[N] int64] on the same device.
     """
-    if tuning is None and sort_model == _capi.SORT_TORCH_CUDA and type(boxes) is torch.Tensor and type(scores) is torch.Tensor \
-            and boxes.dtype == torch.float32 and scores.dtype == torch.float32 and scores.is_contiguous() and boxes.dim() == 2:
-        sh = _capi.shim()
-        if sh is not None:       # the reference's own native signature (nms.cpp:44-48); same checks, same C ABI call
-            return sh.nms_forward(boxes, scores, float(overlap), _as_top_k(top_k))
+    # the per-frame call PHNet makes: straight to the pybind shim -- the reference's own native signature (nms.cpp:44-48), same
+    # checks, same C ABI call; every microsecond of Python here is visible at ~7 us per call
+    if tuning is None and sort_model == 0 and type(boxes) is _Tensor and type(scores) is _Tensor and boxes.dtype is _f32 \
+            and scores.dtype is _f32 and boxes.dim() == 2 and scores.is_contiguous():
+        fwd = _shim_forward if _shim_forward is not None else _bind_shim()
+        if fwd is not False:
+            try:
+                return fwd(boxes, scores, overlap, top_k)
+            except TypeError:
+                pass    # argument types the pybind signature does not take (numpy scalars, negative top_k): the general path below
     boxes, scores = _check_inputs(boxes, scores, batched=False)
     N, P = boxes.shape
     out = torch.empty(2 * N + 1, dtype=torch.int64, device=boxes.device)   # one allocation, three views

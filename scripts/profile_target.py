@@ -12,7 +12,7 @@ from phnet_b200.ops import nms_batched  # noqa: E402
 
 N = int(os.environ.get("N", 1000)); n_off = int(os.environ.get("NOFF", 72)); F = int(os.environ.get("F", 2368))
 top_k = int(os.environ.get("TOPK", 4)); reps = int(os.environ.get("REPS", 4))
-groups = int(os.environ.get("GROUPS", 8)); outl = float(os.environ.get("OUTL", 0.1))
+groups = int(os.environ.get("NGROUPS", os.environ.get("GROUPS", 8))); outl = float(os.environ.get("OUTL", 0.1))
 tune = _capi.tuning(**json.loads(os.environ["TUNE"])) if os.environ.get("TUNE") else None
 dev = torch.device("cuda:0")
 props, scores = synth.make_frames_chunked(F, N, n_off, seed=0, device=dev, groups=groups, outlier_frac=outl)

@@ -112,8 +112,10 @@ def test_plans():
         _capi.plan(4, 1000, 72, _capi.tuning(variant=_capi.FUSED_STREAM), 0)
     small = _capi.plan(8, 1000, 72)             # fewer frames than SMs: frames are cut into units so that every SM has work
     assert small["variant"] == _capi.FUSED_STREAM and small["grid"] > 8
-    one = _capi.plan(1, 240, 72)                # PHNet's own call, one frame: launch-latency bound -> ONE launch (cluster kernel)
-    assert one["variant"] == _capi.FUSED_REG and one["launches"] == 1 and one["cluster"] == 1
+    one = _capi.plan(1, 240, 72)                # PHNet's own call, one frame: launch-latency bound -> ONE launch, no workspace
+    assert one["variant"] == _capi.FUSED_SMALL and one["launches"] == 1 and one["grid"] == 1 and one["workspace_bytes"] == 0
+    mid = _capi.plan(1, 1000, 72)               # one frame of more than 512 proposals: the cluster kernel, still one launch
+    assert mid["variant"] == _capi.FUSED_REG and mid["launches"] == 1
     assert _capi.plan(1, 8192, 72)["path"] == _capi.PATH_FUSED          # the whole stress sweep stays on the fused path
     big = _capi.plan(1, 40000, 72)
     assert big["path"] == _capi.PATH_TILED and big["launches"] == 3 and big["workspace_bytes"] > 0

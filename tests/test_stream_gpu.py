@@ -85,6 +85,16 @@ def test_shapes(cuda_device, N):
             run_both(props, scores, 50.0, top_k, cuda_device, tuning=STREAM, ctx=f"N={N} No={n_off} top_k={top_k}")
 
 
+@pytest.mark.parametrize("N", [1, 2, 5, 7, 8, 9])
+def test_many_frames_of_fewer_proposals_than_one_draw_batch(cuda_device, N):
+    """The automatic plan of a big batch of tiny frames is the streaming path; its draw cap (the whole frame for N <= 256) is
+    then below one batch of 8 draws (found by scripts/soak_random.py: the launch was refused)."""
+    props, scores = synth.make_frames(3000, N, 72, seed=N, groups=2)
+    assert plan(3000, N, 72, top_k=4)["variant"] == _capi.FUSED_STREAM
+    for tuning in (None, STREAM):
+        run_both(props, scores, 50.0, 4, cuda_device, tuning=tuning, ctx=f"tiny frames N={N} tuning={tuning}")
+
+
 @pytest.mark.parametrize("n_off", [72, 36])
 def test_edge_frames_ties_and_sort_models(cuda_device, n_off):
     for seed in range(8):
