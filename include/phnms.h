@@ -157,6 +157,19 @@ int phnms_line_iou_f32(const float *pred, const float *target, int64_t num_pred,
                        float length, int aligned, float *out, void *stream);
 
 /*
+ * The dynamic-k assignment that consumes that matrix: libs/utils/dynamic_assign.py:83-125
+ * `dynamic_k_assign(cost, pair_wise_ious)`; with n_candidate_k / min_k it is also libs/utils/dynamic_assignV2.py:372-405
+ * (max_topk / min_topk), and with binarize != 0 `dynamic_k_assign_CF` (dynamic_assign.py:327-370: IoUs >= binarize_at -> 1, else 0;
+ * the reference uses n_candidate_k 1, min_k 0 there).  cost, iou [B, num_priors, num_gt] fp32 device (B images at once; the
+ * reference takes one).  Writes, per image, count[b] matched priors: prior_idx[b, 0..count) ascending and gt_idx[b, 0..count)
+ * (both [B, num_priors] int64, entries beyond count untouched).  num_priors in [n_candidate_k, 1024], num_gt <= 1024,
+ * n_candidate_k in [1, 8].  Ties between equal costs go to the lowest index (torch.topk leaves them open); no NaNs.
+ */
+int phnms_dynamic_k_assign_f32(const float *cost, const float *iou, int64_t B, int64_t num_priors, int64_t num_gt, int n_candidate_k,
+                               int min_k, int binarize, float binarize_at, int64_t *prior_idx, int64_t *gt_idx, int64_t *count,
+                               void *stream);
+
+/*
  * predictions_to_pred for a whole clip: the tensor part of libs/models/Router4OLV2.py:363-404
  * (hdr == 6) and RouterV4.py:349-392 (hdr == 7) for every kept lane -- start / end rounding, the "extend to the bottom"
  * mask (OpenLane-V models), the -2 fills, selection of the points with x >= 0, the flip, the y rescale (VIL-100 models) --

@@ -16,7 +16,7 @@ EXPORTS = (
     "phnms_abi_version", "phnms_error_string", "phnms_workspace_bytes", "phnms_plan_query", "phnms_plan_query_topk",
     "phnms_forward_f32", "phnms_forward_f32_trace", "phnms_order_workspace_bytes", "phnms_order_f32",
     "phnms_get_lanes_workspace_bytes", "phnms_get_lanes_f32",
-    "phnms_decode_lanes_f32", "phnms_line_iou_f32", "phnms_ordered_f64_workspace_bytes", "phnms_forward_ordered_f64", "phnms_forward_collect_f32", "phnms_peer_alloc", "phnms_peer_open", "phnms_peer_close", "phnms_peer_free", "phnms_peer_sync",
+    "phnms_decode_lanes_f32", "phnms_line_iou_f32", "phnms_dynamic_k_assign_f32", "phnms_ordered_f64_workspace_bytes", "phnms_forward_ordered_f64", "phnms_forward_collect_f32", "phnms_peer_alloc", "phnms_peer_open", "phnms_peer_close", "phnms_peer_free", "phnms_peer_sync",
 )
 ABI_VERSION = 5
 MAX_DST = 16
@@ -135,6 +135,8 @@ def lib() -> ctypes.CDLL:
         L.phnms_decode_lanes_f32.restype = ci
         L.phnms_line_iou_f32.argtypes = [vp, vp, i64, i64, ci, ctypes.c_float, ctypes.c_float, ci, vp, vp]
         L.phnms_line_iou_f32.restype = ci
+        L.phnms_dynamic_k_assign_f32.argtypes = [vp, vp, i64, i64, i64, ci, ci, ci, ctypes.c_float, vp, vp, vp, vp]
+        L.phnms_dynamic_k_assign_f32.restype = ci
         L.phnms_ordered_f64_workspace_bytes.argtypes = [i64, i64]
         L.phnms_ordered_f64_workspace_bytes.restype = sz
         L.phnms_forward_ordered_f64.argtypes = [vp, vp, vp, i64, i64, ci, ctypes.c_float, i64, vp, vp, vp, vp, sz, vp]

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libphnms.so")
 SOURCES = ["phnms.cu"]
-HEADERS = ["common.cuh", "fused_nms.cuh", "fused_reg.cuh", "topm.cuh", "select.cuh", "stream.cuh", "small.cuh", "tiled_nms.cuh", "frontend.cuh",
+HEADERS = ["common.cuh", "fused_nms.cuh", "fused_reg.cuh", "topm.cuh", "select.cuh", "stream.cuh", "small.cuh", "assign.cuh", "tiled_nms.cuh", "frontend.cuh",
            os.path.join("..", "..", "include", "phnms.h")]
 
 NVCC_FLAGS = [
@@ -42,7 +42,10 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     if not force and not stale():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (extra or []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    # (written next to the target and renamed over it: a process that has the old library mapped -- pytest after a header edit --
+    # keeps its old inode instead of seeing the file change under its feet)
+    tmp_so = SO + f".tmp{os.getpid()}"
+    cmd = [nvcc()] + NVCC_FLAGS + (extra or []) + ["-o", tmp_so] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -52,7 +55,10 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
         print(res.stdout)
         print(res.stderr)
     if res.returncode != 0:
+        if os.path.exists(tmp_so):
+            os.remove(tmp_so)
         raise RuntimeError("nvcc failed building libphnms.so")
+    os.replace(tmp_so, SO)
     return SO
 
 
@@ -73,22 +79,32 @@ def build_shim(force: bool = False, verbose: bool = False) -> str:
     cpp_extension (host compiler only, ~1 min); needs libphnms.so next to it at run time ($ORIGIN rpath)."""
     if not force and not shim_stale():
         return SHIM_SO
+    import sys
     import tempfile
-    from torch.utils.cpp_extension import load
     if not os.path.exists(SO):
         build()
     tmp = tempfile.mkdtemp(prefix="phnms_shim_")
+    # Built in a CHILD process: cpp_extension.load() also dlopens what it built, and a second copy of the module loaded into a
+    # process that already holds one (pytest after phnet_b200 imported its shim) crashed the interpreter.
+    code = (
+        "import os, sys\n"
+        "from torch.utils.cpp_extension import load\n"
+        "os.environ.setdefault('MAX_JOBS', '4')\n"
+        "try:\n"
+        "    load(name='nms_impl', sources=[sys.argv[1]], extra_cflags=['-O2'], with_cuda=True,\n"
+        "         extra_ldflags=['-L' + sys.argv[2], '-l:libphnms.so', '-Wl,-rpath,\\\\$$ORIGIN'],\n"
+        "         build_directory=sys.argv[3], is_python_module=False, verbose=bool(int(sys.argv[4])))\n"
+        "except OSError:\n"
+        "    pass\n"   # built, but not loadable from the temporary directory: libphnms.so is found through $ORIGIN, i.e. next to it
+    )
     try:
-        os.environ.setdefault("MAX_JOBS", "4")
-        try:
-            load(name="nms_impl", sources=[SHIM_SRC], extra_cflags=["-O2"], with_cuda=True,
-                 extra_ldflags=[f"-L{CSRC}", "-l:libphnms.so", "-Wl,-rpath,\\$$ORIGIN"],
-                 build_directory=tmp, is_python_module=False, verbose=verbose)
-        except OSError:
-            pass    # built, but not loadable from the temporary directory: libphnms.so is found through $ORIGIN, i.e. next to it
+        res = subprocess.run([sys.executable, "-c", code, SHIM_SRC, CSRC, tmp, "1" if verbose else "0"], capture_output=not verbose, text=True)
         if not os.path.exists(os.path.join(tmp, "nms_impl.so")):
+            if res.stdout or res.stderr:
+                print(res.stdout, res.stderr)
             raise RuntimeError("building the nms_impl shim failed")
-        shutil.copy(os.path.join(tmp, "nms_impl.so"), SHIM_SO)
+        shutil.copy(os.path.join(tmp, "nms_impl.so"), SHIM_SO + f".tmp{os.getpid()}")
+        os.replace(SHIM_SO + f".tmp{os.getpid()}", SHIM_SO)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return SHIM_SO

@@ -19,6 +19,7 @@
 #include "stream.cuh"
 #include "frontend.cuh"
 #include "small.cuh"
+#include "assign.cuh"
 
 using namespace phnms;
 
@@ -1057,6 +1058,23 @@ int phnms_line_iou_f32(const float *pred, const float *target, int64_t num_pred,
     }
     phnms_line_iou_kernel<<<(unsigned)((num_pred + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
         pred, target, (int)num_pred, (int)num_target, n_off, img_w, length, aligned, out);
+    return (int)cudaGetLastError();
+}
+
+int phnms_dynamic_k_assign_f32(const float *cost, const float *iou, int64_t B, int64_t num_priors, int64_t num_gt, int n_candidate_k,
+                               int min_k, int binarize, float binarize_at, int64_t *prior_idx, int64_t *gt_idx, int64_t *count,
+                               void *stream) {
+    if (B < 0 || num_gt < 0 || num_gt > kAssignMaxGt || n_candidate_k < 1 || n_candidate_k > kAssignMaxCand || min_k < 0 ||
+        num_priors < n_candidate_k || num_priors > kAssignMaxPriors || B > 0x7fffffff)
+        return PHNMS_ERR_BAD_ARG;
+    if (B == 0) return PHNMS_OK;
+    if (!count || !prior_idx || !gt_idx) return PHNMS_ERR_BAD_ARG;
+    if (num_gt == 0) return (int)cudaMemsetAsync(count, 0, (size_t)B * 8, (cudaStream_t)stream);
+    if (!cost || !iou) return PHNMS_ERR_BAD_ARG;
+    const int threads = (int)((num_priors + 31) / 32) * 32;
+    phnms_dynamic_k_assign_kernel<<<(unsigned)B, threads < 64 ? 64 : threads, (size_t)num_gt * sizeof(int), (cudaStream_t)stream>>>(
+        cost, iou, (int)num_priors, (int)num_gt, n_candidate_k, min_k, binarize, binarize_at,
+        reinterpret_cast<long long *>(prior_idx), reinterpret_cast<long long *>(gt_idx), reinterpret_cast<long long *>(count));
     return (int)cudaGetLastError();
 }
 

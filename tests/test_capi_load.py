@@ -198,7 +198,11 @@ def _reference_style_package(tmp_path):
     (pkg / "__init__.py").write_text("from .nms import nms\n__all__ = ['nms']\n")
     (pkg / "nms.py").write_text("from . import nms_impl\n\n\ndef nms(boxes, scores, overlap, top_k):\n"
                                 "    return nms_impl.nms_forward(boxes, scores, overlap, top_k)\n")
-    os.symlink(build.SHIM_SO, pkg / "nms_impl.so")
+    # a COPY, as a maintainer would install it -- and a separate file is a separate dlopen instance: initialising one pybind11
+    # module object twice in a process (a symlink to the file phnet_b200 itself loads) re-runs PyInit on the same static
+    # PyModuleDef, which crashed the interpreter depending on test order
+    import shutil
+    shutil.copy(build.SHIM_SO, pkg / "nms_impl.so")
     os.symlink(build.SO, pkg / "libphnms.so")
     return str(tmp_path)
 
