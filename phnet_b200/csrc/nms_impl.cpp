@@ -95,6 +95,18 @@ std::vector<at::Tensor> nms_forward(at::Tensor boxes, at::Tensor scores, float t
     return forward_batched(boxes, scores, c10::nullopt, (double)thresh, (int64_t)top_k, PHNMS_SORT_TORCH_CUDA, true);
 }
 
+// The same call for phnet_b200.ops.nms: None instead of an exception when the arguments are not the plain float32 case, so that
+// the Python wrapper needs no checks of its own on the fast path (each attribute lookup there is ~0.1 us of a ~7 us call) and
+// sends everything else -- double boxes, strided scores, CPU tensors (which must raise the reference's errors) -- down its
+// general path.
+pybind11::object nms_forward_or_none(const at::Tensor &boxes, const at::Tensor &scores, double thresh, int64_t top_k) {
+    if (!boxes.is_cuda() || !scores.is_cuda() || boxes.scalar_type() != at::kFloat || scores.scalar_type() != at::kFloat ||
+        boxes.dim() != 2 || scores.dim() != 1 || !boxes.is_contiguous() || !scores.is_contiguous() || top_k < 0 || boxes.size(1) < 6 ||
+        scores.size(0) != boxes.size(0) || scores.device() != boxes.device())
+        return pybind11::none();
+    return pybind11::cast(forward_batched(boxes, scores, c10::nullopt, thresh, top_k, PHNMS_SORT_TORCH_CUDA, true));
+}
+
 std::vector<at::Tensor> nms_forward_batched(at::Tensor boxes, at::Tensor scores, c10::optional<at::Tensor> n_valid, double thresh,
                                             int64_t top_k, int64_t sort_model) {
     return forward_batched(boxes, scores, n_valid, thresh, top_k, sort_model, false);
@@ -107,5 +119,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("nms_forward_batched", &nms_forward_batched, "F independent nms_forward calls in one launch",
           pybind11::arg("boxes"), pybind11::arg("scores"), pybind11::arg("n_valid") = pybind11::none(), pybind11::arg("thresh") = 50.0,
           pybind11::arg("top_k") = 4, pybind11::arg("sort_model") = 0);
+    m.def("nms_forward_or_none", &nms_forward_or_none, "nms_forward, or None when the arguments are not the plain float32 CUDA case");
     m.def("abi_version", []() { return phnms_abi_version(); });
 }

@@ -81,7 +81,7 @@ int ensure_max_smem(const void *kern, int smem_optin) {
 
 // experiment knobs of debug sessions, read once at load (never on the call path)
 struct EnvKnobs {
-    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, no_small, debug, skip, small_batch;
+    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, no_small, small_grid_f, debug, skip, small_batch;
     EnvKnobs() {
         auto geti = [](const char *n) { const char *v = getenv(n); return v ? atoi(v) : 0; };
         topm_count = geti("PHNMS_TOPM_COUNT");
@@ -92,6 +92,7 @@ struct EnvKnobs {
         stream_cpt = geti("PHNMS_STREAM_CPT");
         no_stream = getenv("PHNMS_NO_STREAM") != nullptr;
         no_small = getenv("PHNMS_NO_SMALL") != nullptr;
+        small_grid_f = getenv("PHNMS_SMALL_GRID_F") != nullptr;   // experiment: one CTA per frame instead of persistent CTAs
         debug = getenv("PHNMS_DEBUG") != nullptr;
         small_batch = getenv("PHNMS_SMALL_BATCH") ? geti("PHNMS_SMALL_BATCH") : -1;
         skip = geti("PHNMS_SKIP");   // timing experiments only (results are wrong): 1 = no select, 2 = no stream, 4 = no resume
@@ -119,6 +120,7 @@ size_t tiled_workspace(int64_t F, int64_t N) {
 }
 
 constexpr long long kSmallBatchProposals = 2048;
+constexpr int kSmallAnyBatchN = 256;   // frames up to this size take the one-launch kernel (small.cuh) whatever the batch size
 constexpr int kSelFullScanN = 256;   // F * N at or below this: single-launch path (see make_plan)
 
 // Launch shape of the streaming kernel (stream.cuh): warps per CTA, how frames are cut into units when there are fewer
@@ -216,19 +218,36 @@ int make_plan(int64_t F, int64_t N, int n_off, int64_t top_k, const phnms_tuning
         const bool want_stream = t.variant == PHNMS_FUSED_STREAM ||
                                  (t.variant == 0 && !t.cluster && !t.threads && !t.schedule && !g_env.no_stream && !small);
         if (t.variant == PHNMS_FUSED_STREAM && (!reg_ok || !k_ok || t.cluster || t.threads || t.schedule)) return PHNMS_ERR_TUNING;
-        // ... and when its frames have at most 512 proposals, the one-launch kernel of small.cuh: one CTA per frame, no workspace
+        // ... and when its frames have at most 512 proposals, the one-launch kernel of small.cuh: one CTA per frame, no workspace.
+        // Frames of at most 256 proposals (everything PHNet itself produces: 240 priors) take it whatever the batch size: persistent
+        // CTAs, the next frame's rows in flight during the greedy rounds of the current one; its cost does not depend on where in
+        // the order the kept lanes sit, and any top_k goes (measured against select -> stream at N = 240: 0.68 vs 0.56-0.66 of the
+        // roofline at 72 offsets / top_k 4, 0.32 vs 0.22-0.27 at 36 offsets / top_k 8, before the prefetch).
         const bool small_ok = reg_ok && N <= kSmallMaxN && !t.cluster && !t.threads && !t.schedule;
         if (t.variant == PHNMS_FUSED_SMALL && !small_ok) return PHNMS_ERR_TUNING;
-        if (small_ok && (t.variant == PHNMS_FUSED_SMALL || (small && !g_env.no_small)) && F <= 0x7fffffff) {
+        if (small_ok && (t.variant == PHNMS_FUSED_SMALL || (t.variant == 0 && !g_env.no_small && (small || N <= kSmallAnyBatchN))) &&
+            F <= 0x7fffffff) {
             const int warps = N > 32 ? (int)((N + 31) / 32) : 1;
+            const int smem = small_layout(warps, P).total;
+            // resident CTAs per SM: shared memory, registers (128 per thread; 80 for <= 256 threads at 36 offsets), threads
+            const int regs = (n_off == 36 && warps <= 8) ? 80 : 128;
+            int per_sm = (smem_max + 1024) / (smem + 1024);
+            if (per_sm > 65536 / (warps * 32 * regs)) per_sm = 65536 / (warps * 32 * regs);
+            if (per_sm > 2048 / (warps * 32)) per_sm = 2048 / (warps * 32);
+            if (per_sm > 32) per_sm = 32;
+            if (per_sm < 1) per_sm = 1;
+            long long grid = g_env.small_grid_f ? (long long)F : (long long)per_sm * sms;
+            if (t.max_clusters > 0 && grid > t.max_clusters) grid = t.max_clusters;
+            if (grid > F) grid = F;
+            if (grid < 1) grid = 1;
             pl->path = PHNMS_PATH_FUSED;
             pl->variant = PHNMS_FUSED_SMALL;
             pl->cluster = 1;
             pl->threads = warps * 32;
             pl->rows_per_cta = warps * 32;
-            pl->smem_bytes = small_layout(warps, P).total;
-            pl->grid = (int)(F > 0 ? F : 1);
-            pl->max_active_clusters = pl->grid;
+            pl->smem_bytes = smem;
+            pl->grid = (int)grid;
+            pl->max_active_clusters = (int)((long long)per_sm * sms);
             return PHNMS_OK;
         }
         if (reg_ok) {
@@ -807,15 +826,16 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
         q.num_keep = reinterpret_cast<long long *>(num_keep);
         q.parent = reinterpret_cast<long long *>(parent);
         q.F = F; q.top_k = top_k; q.N = (int)N; q.sort_model = sort_model; q.thr = thresh;
-        if (n_off == 72) {
-            rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<72>), dev.smem_optin);
-            if (rc) return fail_at("small smem attribute", rc);
-            phnms_small_kernel<72><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q);
-        } else {
-            rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<36>), dev.smem_optin);
-            if (rc) return fail_at("small smem attribute", rc);
-            phnms_small_kernel<36><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q);
-        }
+#define PHNMS_LAUNCH_SMALL(NO, MT, MB)                                                                                  \
+    do {                                                                                                              \
+        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<NO, MT, MB>), dev.smem_optin);         \
+        if (rc) return fail_at("small smem attribute", rc);                                                           \
+        phnms_small_kernel<NO, MT, MB><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q);          \
+    } while (0)
+        if (n_off == 72) PHNMS_LAUNCH_SMALL(72, 512, 1);
+        else if (pl.threads <= 256) PHNMS_LAUNCH_SMALL(36, 256, 3);
+        else PHNMS_LAUNCH_SMALL(36, 512, 1);
+#undef PHNMS_LAUNCH_SMALL
         return fail_at("small launch", (int)cudaGetLastError());
     }
     if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_STREAM)

@@ -1,6 +1,6 @@
 """Randomised soak: ITER (default 10 000) launches over random configurations of the lane-NMS op -- shape, offset count, top_k,
 threshold, generator (lane groups, outliers, ties), ragged n_valid, device algorithm (auto / streaming with random warps, lanes
-per pass and draw cap / cluster kernels with random cluster size and schedule / tiled), stream -- each checked bit for bit
+per pass and draw cap / the one-launch small-frame kernel with random grids / cluster kernels with random cluster size and schedule / tiled), stream -- each checked bit for bit
 against the CPU oracle on a sample of its frames, and every configuration launched three times in a row with identical results.
 A hang becomes a failed launch (mbarrier waits are bounded, common.cuh), a race a mismatch.  Prints one line per 500 launches.
 
@@ -29,7 +29,7 @@ while launches < iters:
     top_k = rng.choice([1, 2, 3, 4, 4, 4, 5, 8, 8, 0, N])
     thr = rng.choice([10.0, 20.0, 30.0, 40.0, 50.0, 50.0])
     groups, outl, ties = rng.choice([1, 2, 3, 4, 8]), rng.choice([0.0, 0.01, 0.1]), rng.random() < 0.2
-    kind = rng.choice(["auto", "auto", "stream", "stream", "cluster", "tiled"])
+    kind = rng.choice(["auto", "auto", "stream", "stream", "cluster", "tiled", "small"])
     tune = None
     if kind == "stream" and 1 <= top_k <= 8:
         tune = dict(variant=3, stream_warps=rng.choice([0, 1, 3, 8, 16]), lanes_per_pass=rng.choice([0, 1, 2, 4]),
@@ -38,6 +38,8 @@ while launches < iters:
         tune = dict(path=1, variant=rng.choice([1, 2]), cluster=rng.choice([0, 0, 1, 2, 4, 8]), schedule=rng.choice([0, 1, 2]))
     elif kind == "tiled":
         tune = dict(path=2)
+    elif kind == "small" and N <= 512:
+        tune = dict(variant=4, max_clusters=rng.choice([0, 0, 1, 5, 148]))
     if tune is not None:
         try:
             _capi.plan(F, N, n_off, _capi.tuning(**tune), top_k)

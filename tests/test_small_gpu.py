@@ -29,7 +29,9 @@ def test_plan_small_calls_take_the_one_launch_kernel(cuda_device):
                 pl = plan(F, N, n_off, top_k=top_k)
                 assert pl["variant"] == _capi.FUSED_SMALL and pl["launches"] == 1 and pl["workspace_bytes"] == 0 and pl["grid"] == F, pl
         assert plan(1, 513, n_off, top_k=4)["variant"] != _capi.FUSED_SMALL          # more than 512 proposals per frame
-        assert plan(16, 240, n_off, top_k=4)["variant"] == _capi.FUSED_STREAM        # more than 2048 proposals in the call
+        assert plan(16, 300, n_off, top_k=4)["variant"] == _capi.FUSED_STREAM        # more than 2048 proposals in the call, N > 256
+        big = plan(100000, 240, n_off, top_k=4)     # frames of <= 256 proposals: this kernel whatever the batch size, persistent CTAs
+        assert big["variant"] == _capi.FUSED_SMALL and big["launches"] == 1 and 148 <= big["grid"] <= 148 * 8
     assert plan(1, 240, 50, top_k=4)["variant"] == _capi.FUSED_SMEM                  # other offset counts: the shared-memory kernel
     with pytest.raises(_capi.PhnmsError):
         plan(4, 600, 72, tuning=SMALL)
@@ -99,13 +101,37 @@ def test_ragged_and_misaligned(cuda_device):
 def test_forced_on_big_batches_agrees_with_the_streaming_path_and_repeats(cuda_device, N, n_off, top_k):
     F = 3000
     props, scores = synth.make_frames_chunked(F, N, n_off, seed=N + top_k, device=cuda_device, groups=3)
-    ref = nms_batched(props, scores, 50.0, top_k)     # the automatic plan (streaming / cluster kernels)
+    other = dict(variant=_capi.FUSED_STREAM) if 1 <= top_k <= 8 else dict(path=1, variant=_capi.FUSED_REG)
+    ref = nms_batched(props, scores, 50.0, top_k, tuning=other)     # the streaming / cluster kernels
     for rep in range(3):
-        got = nms_batched(props, scores, 50.0, top_k, tuning=SMALL)
+        got = nms_batched(props, scores, 50.0, top_k, tuning=SMALL if rep else dict(variant=_capi.FUSED_SMALL, max_clusters=5))
         for x, y in zip(got, ref):
             assert torch.equal(x, y), f"N={N} No={n_off} top_k={top_k} rep={rep}"
     idx = torch.arange(0, F, 131)
     assert_same([t[idx] for t in ref], oracle_batched(props[idx].cpu(), scores[idx].cpu(), 50.0, top_k), f"oracle sample N={N}")
+
+
+@pytest.mark.parametrize("n_off", [72, 36])
+def test_persistent_ctas_over_ragged_frames(cuda_device, n_off):
+    """Many frames per CTA (max_clusters caps the grid), every frame with its own number of real proposals -- warps whose slice of a
+    frame is empty skip that frame's load, so the per-warp barrier phases advance at different rates -- on a side stream, from
+    tensors that are only 4-byte aligned."""
+    F, N = 2000, 250
+    g = torch.Generator().manual_seed(n_off)
+    props, scores = synth.make_frames(F, N, n_off, seed=21, groups=3)
+    n_valid = torch.randint(0, N + 1, (F,), generator=g, dtype=torch.int32)
+    n_valid[:8] = torch.tensor([0, 0, 1, N, 32, 33, 0, 64], dtype=torch.int32)
+    P = 5 + n_off
+    big = torch.zeros(F * N * P + 1, device=cuda_device)[1:].view(F, N, P)
+    big.copy_(props)
+    want = oracle_batched(props, scores, 50.0, 4, n_valid)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for cap in (0, 1, 7, 148):
+            got = nms_batched(big, scores.to(cuda_device), 50.0, 4, n_valid.to(cuda_device), tuning=dict(variant=_capi.FUSED_SMALL, max_clusters=cap))
+            st.synchronize()
+            assert_same(got, want, f"ragged persistent No={n_off} max_clusters={cap}")
 
 
 def test_subnormal_offsets_and_thresholds(cuda_device):

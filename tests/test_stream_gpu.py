@@ -87,10 +87,10 @@ def test_shapes(cuda_device, N):
 
 @pytest.mark.parametrize("N", [1, 2, 5, 7, 8, 9])
 def test_many_frames_of_fewer_proposals_than_one_draw_batch(cuda_device, N):
-    """The automatic plan of a big batch of tiny frames is the streaming path; its draw cap (the whole frame for N <= 256) is
-    then below one batch of 8 draws (found by scripts/soak_random.py: the launch was refused)."""
+    """Forced onto the streaming path, the draw cap of a tiny frame (the whole frame for N <= 256) is below one batch of 8 draws
+    (found by scripts/soak_random.py: the launch was refused).  (The automatic plan of such a batch is the one-launch kernel.)"""
     props, scores = synth.make_frames(3000, N, 72, seed=N, groups=2)
-    assert plan(3000, N, 72, top_k=4)["variant"] == _capi.FUSED_STREAM
+    assert plan(3000, N, 72, top_k=4)["variant"] == _capi.FUSED_SMALL
     for tuning in (None, STREAM):
         run_both(props, scores, 50.0, 4, cuda_device, tuning=tuning, ctx=f"tiny frames N={N} tuning={tuning}")
 
