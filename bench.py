@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--groups", type=int, default=8, help="lane groups per synthetic frame (2-4 = road-like; PHNet max_lanes is 4)")
     ap.add_argument("--outlier-frac", type=float, default=0.1, help="fraction of proposals that belong to no lane group")
-    ap.add_argument("--variant", type=int, default=0, help="0 auto, 2 register-resident cluster kernel, 3 streaming path")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 2 register-resident cluster kernel, 3 streaming path, 4 one-launch small-frame kernel")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA op (oracle/_ref)")
     return ap.parse_args()
 
@@ -473,6 +473,7 @@ def run_ours(a):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": bpf,
                          "kernel": ("phnms_select_kernel + phnms_stream_kernel + resume pass (one C-ABI call; the stream kernel is ~90 % of it, profiles/)" if plan.get("variant") == 3
+                                    else "phnms_small_kernel (one launch: persistent CTAs, one frame at a time, rows in registers)" if plan.get("variant") == 4
                                     else "phnms_topm_kernel + phnms_freg_kernel (one C-ABI call)" if plan.get("variant") == 2
                                     else "phnms_fused_kernel" if plan["path"] == 1 else "phnms_order/mask/scan kernels"),
                          "kernel_ms_per_launch": kern_ms, "kernel_ms_median": kern_median, "kernel_ms_min": kern_min,

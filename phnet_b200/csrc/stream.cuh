@@ -316,6 +316,9 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
             if (nrows > 0) {
                 mbar_wait(bar_rows, rphase);
                 rphase ^= 1u;
+            }
+            {   // (an item without rows reads whatever the slot holds: nothing of it is used -- its lanes are not `real` -- and an
+                // else-branch that zeroes 72 registers costs every item 36 instructions)
                 const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)cur.f * sp.N + cur.r0) * P);
                 const uint32_t row = slot_s + 128u + (uint32_t)(a0 & 15) + (uint32_t)(lane < nrows ? lane : 0) * (P * 4);
 #pragma unroll
@@ -323,12 +326,6 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
                 st[0] = lane_start(__uint_as_float(lds_u32(row + 8u)), NOFF);            // nms_kernel.cu:29-30
                 en[0] = lane_end(__uint_as_float(lds_u32(row + 16u)), st[0], NOFF);      // :32-34
                 score = __uint_as_float(lds_u32(slot_s + 4u * (uint32_t)(lane < nrows ? lane : 0)));
-            } else {
-#pragma unroll
-                for (int i = 0; i < NOFF; ++i) x[0][i] = 0.0f;
-                st[0] = 0;
-                en[0] = -1;
-                score = 0.0f;
             }
             __syncwarp();   // every lane has read its row: the slot is free for the next item
             // advance to this warp's next item slot and request it

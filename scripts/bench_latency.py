@@ -43,6 +43,15 @@ def main():
                 out[key + "_calls_per_s"] = round(F / dt, 1)
                 if not sync:
                     out[key + "_gpu_us_per_call"] = round(e0.elapsed_time(e1) * 1e3 / F, 2)
+            # the same async burst over frames sliced beforehand (get_lanes hands over freshly filtered tensors, not views it
+            # indexes per call): the op call alone
+            ps, ss = [props[f] for f in range(F)], [scores[f] for f in range(F)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for f in range(F):
+                fn(ps[f], ss[f], 50.0, top_k)
+            torch.cuda.synchronize()
+            out[f"{name}_N{N}_No{n_off}_k{top_k}_async_presliced_calls_per_s"] = round(F / (time.perf_counter() - t0), 1)
     print(json.dumps(out))
 
 

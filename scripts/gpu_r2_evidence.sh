@@ -10,27 +10,19 @@ for g in 2 3 4; do timeout 200 python bench.py --groups $g --no-e2e --no-cpu-bas
 timeout 200 python bench.py --top-k 8 --no-e2e --no-cpu-baseline --no-ref-cuda --steps 30 > gpurun_out/r2_bench_topk8.json 2>> gpurun_out/r2_bench.err
 # BASELINE config 3 (VIL-100: 240 priors x 36 offsets, top_k 8) and config 4 (sweep points)
 timeout 200 python bench.py --proposals 240 --offsets 36 --top-k 8 --frames 65536 --e2e-frames 8192 --no-cpu-baseline --steps 30 > gpurun_out/r2_bench_config3_vil.json 2>> gpurun_out/r2_bench.err
+: > gpurun_out/r2_bench_config4_sweep.jsonl
 for n in 256 2048 8192; do for thr in 10 30 50; do
   timeout 200 python bench.py --proposals $n --overlap $thr --frames $((16384*1000/n)) --no-e2e --no-cpu-baseline --no-ref-cuda --steps 20 >> gpurun_out/r2_bench_config4_sweep.jsonl 2>> gpurun_out/r2_bench.err
 done; done
 timeout 200 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r2_bench_reference_arm.json 2>> gpurun_out/r2_bench.err
+rm -f gpurun_out/r2_bench_config4_sweep.jsonl.tmp
 # launch list of the bench command
 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-ref-cuda > gpurun_out/r2_bench_s2.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:phnms -c 30 --csv --log-file gpurun_out/r2_bench_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-ref-cuda > gpurun_out/r2_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# full captures
-cap() { # name, kernel regex, env...
-  name=$1; shift; kre=$1; shift
-  env "$@" python scripts/profile_target.py > gpurun_out/r2_prof_plain_$name.log 2>&1 &&
-  env "$@" ncu --set full --clock-control none --import-source on -k regex:$kre -s 4 -c 1 -f -o gpurun_out/r2_$name python scripts/profile_target.py > gpurun_out/r2_ncu_$name.log 2>&1
-  echo "ncu $name rc=$?"
-}
-cap stream_72_k4 stream F=16384 N=1000 NOFF=72 TOPK=4
-cap select_72_k4 select F=16384 N=1000 NOFF=72 TOPK=4
-cap stream_72_k8 stream F=16384 N=1000 NOFF=72 TOPK=8
-cap stream_36_k8 stream F=16384 N=1000 NOFF=36 TOPK=8
-cap stream_4096 stream F=2048 N=4096 NOFF=72 TOPK=4
-cap stream_72_g2 stream F=16384 N=1000 NOFF=72 TOPK=4 GROUPS=2
+# (full ncu captures: scripts/gpu_r2_ncu.sh)
 timeout 200 python scripts/bench_latency.py > gpurun_out/r2_latency.json 2>/dev/null; echo "latency rc=$?"
+timeout 200 python scripts/bench_latency_detail.py 2>/dev/null | tail -1 > gpurun_out/r2_latency_detail.json
+printf "1000 72 4 16384 8 0.1\n1000 72 4 16384 2 0.1\n1000 72 8 16384 8 0.1\n1000 36 8 16384 8 0.1\n240 72 4 32768 3 0.1\n240 36 8 32768 3 0.1\n4096 72 4 2048 8 0.1\n" | bash scripts/gpu_r2_split.sh > /dev/null
 timeout 300 python scripts/bench_get_lanes.py > gpurun_out/r2_get_lanes_decode_bench.log 2>&1; echo "get_lanes rc=$?"

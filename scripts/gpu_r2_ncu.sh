@@ -9,15 +9,19 @@ cap() { # name, kernel regex, env...
   echo "ncu $name rc=$?"
 }
 # (each report is ~11 MB and one call may bring back 64 MB: two parts)
-if [ "$PART" != "b" ]; then
+if [ "$PART" = "a" ] || [ "$PART" = "all" ]; then
 cap stream_72_k4 stream F=16384 N=1000 NOFF=72 TOPK=4
 cap select_72_k4 select F=16384 N=1000 NOFF=72 TOPK=4
 cap stream_72_k8 stream F=16384 N=1000 NOFF=72 TOPK=8
 fi
-if [ "$PART" != "a" ]; then
+if [ "$PART" = "b" ] || [ "$PART" = "all" ]; then
 cap stream_36_k8 stream F=16384 N=1000 NOFF=36 TOPK=8
 cap stream_4096 stream F=2048 N=4096 NOFF=72 TOPK=4
-cap stream_72_g2 stream F=16384 N=1000 NOFF=72 TOPK=4 GROUPS=2
+cap stream_72_g2 stream F=16384 N=1000 NOFF=72 TOPK=4 NGROUPS=2
+fi
+if [ "$PART" = "c" ] || [ "$PART" = "all" ]; then      # the one-launch small-frame kernel on PHNet's own shapes
+cap small_240_72_k4 small F=32768 N=240 NOFF=72 TOPK=4 NGROUPS=3
+cap small_240_36_k8 small F=32768 N=240 NOFF=36 TOPK=8 NGROUPS=3
 fi
 # one-frame calls: device time of the single launch
 F=1 N=240 NOFF=72 TOPK=4 REPS=20 python scripts/profile_target.py > /dev/null 2>&1 &&

@@ -44,7 +44,8 @@ shapes = [
     (1000, 72, 4, 16384, 1, 0.1), (1000, 72, 4, 16384, 2, 0.0), (1000, 72, 4, 16384, 3, 0.01),
     # top_k = 8 (VIL-100: optionsV3.py:89-91)
     (1000, 72, 8, 16384, 8, 0.1), (1000, 36, 8, 16384, 8, 0.1), (240, 36, 8, 32768, 8, 0.1), (240, 36, 8, 32768, 3, 0.1),
-    (1000, 36, 4, 16384, 8, 0.1), (240, 72, 4, 32768, 8, 0.1), (240, 72, 4, 32768, 3, 0.1),
+    (1000, 36, 4, 16384, 8, 0.1), (240, 72, 4, 32768, 8, 0.1), (240, 72, 4, 32768, 3, 0.1), (240, 36, 4, 32768, 3, 0.1),
+    (100, 72, 4, 65536, 4, 0.1),
     # stress sweep sizes (BASELINE config 4)
     (256, 72, 4, 32768, 8, 0.1), (512, 72, 4, 16384, 8, 0.1), (2048, 72, 4, 4096, 8, 0.1), (4096, 72, 4, 2048, 8, 0.1),
     (8192, 72, 4, 1024, 8, 0.1),
