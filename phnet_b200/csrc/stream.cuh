@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
                 rphase ^= 1u;
             }
             {   // (an item without rows reads whatever the slot holds: nothing of it is used -- its lanes are not `real` -- and an
-                // else-branch that zeroes 72 registers costs every item 36 instructions)
+                // else-branch that zeroes 72 registers costs every item 36 instructions; A/B on one box: 0.829 -> 0.849 of the roofline
+                // at the headline shape, 0.75 -> 0.78 at 36 offsets)
                 const uintptr_t a0 = (uintptr_t)(sp.props + ((size_t)cur.f * sp.N + cur.r0) * P);
                 const uint32_t row = slot_s + 128u + (uint32_t)(a0 & 15) + (uint32_t)(lane < nrows ? lane : 0) * (P * 4);
 #pragma unroll
