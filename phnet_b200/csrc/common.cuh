@@ -228,20 +228,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  : "memory");
 }
 
-// The same copy with an L2 evict-first hint: rows that are read exactly once should not push the small reused data (kept-lane
-// blocks, scores) out of L2.
-__device__ __forceinline__ void bulk_g2s_stream(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-#ifdef PHNMS_NO_EVICT_FIRST
-    bulk_g2s(dst, src, bytes, bar);
-#else
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
-                 : "memory");
-#endif
-}
-
 __device__ __forceinline__ void st_global_cs_u64(long long *p, long long v) {  // streaming store: outputs are write-once
     asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }

@@ -143,9 +143,10 @@ StreamShape stream_shape(int64_t F, int64_t N, int n_off, int64_t top_k, const p
     // measured slower: 0.64 vs 0.73 of the roofline at N = 1000, top_k = 4.)
     ss.cpt = 1;
     ss.lanes = t.lanes_per_pass ? t.lanes_per_pass : g_env.lanes_per_pass;
-    // measured (N = 1000): 72 offsets: 2 lanes per pass 0.86 of the roofline, 4 lanes 0.78 (spills); 36 offsets: 4 lanes 0.775, 2 lanes 0.76
+    // measured (N = 1000): 72 offsets: 2 lanes per pass 0.86 of the roofline, 4 lanes 0.78 (spills); 36 offsets: 4 lanes 0.775, 2 lanes 0.76;
+    // three lanes per pass (top_k 5..8) spill as well: 0.46 vs 0.54 at top_k 8, 0.65 vs 0.71 at top_k 5
     if (ss.lanes == 0) ss.lanes = (top_k >= 0 && top_k < 2) ? 1 : ((n_off == 36 && (top_k < 0 || top_k >= 4)) ? 4 : 2);
-    if (ss.lanes < 1 || ss.lanes > 4) {
+    if (ss.lanes != 1 && ss.lanes != 2 && ss.lanes != 4) {
         ss.bad_tuning = true;
         return ss;
     }
@@ -752,12 +753,10 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
     do {                                                                                                              \
         if (general) {                                                                                                \
             if (lanes == 4) PHNMS_LAUNCH_STREAM(NO, 4, true);                                                         \
-            else if (lanes == 3) PHNMS_LAUNCH_STREAM(NO, 3, true);                                                    \
             else if (lanes == 2) PHNMS_LAUNCH_STREAM(NO, 2, true);                                                    \
             else PHNMS_LAUNCH_STREAM(NO, 1, true);                                                                    \
         } else {                                                                                                      \
             if (lanes == 4) PHNMS_LAUNCH_STREAM(NO, 4, false);                                                        \
-            else if (lanes == 3) PHNMS_LAUNCH_STREAM(NO, 3, false);                                                   \
             else if (lanes == 2) PHNMS_LAUNCH_STREAM(NO, 2, false);                                                   \
             else PHNMS_LAUNCH_STREAM(NO, 1, false);                                                                   \
         }                                                                                                             \

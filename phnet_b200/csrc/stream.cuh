@@ -243,16 +243,16 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32, 1) phnms_stream_kernel(c
         const uintptr_t a0 = (uintptr_t)src;
         const uint32_t bytes = (uint32_t)nrows * (P * 4);
         if (((a0 | bytes) & 15u) == 0u) {   // the usual case: N a multiple of 4 and an aligned tensor
-            if (lane == 0) {
+            if (lane == 0) {   // (an L2 evict-first hint on this copy was measured: no gain at N = 1000, -3 % at N = 2048 / 4096)
                 mbar_arrive_expect_tx(bar_rows, bytes);
-                bulk_g2s_stream(slot_s + 128u, src, bytes, bar_rows);
+                bulk_g2s(slot_s + 128u, src, bytes, bar_rows);
             }
         } else {
             const uintptr_t b0 = (a0 + 15) & ~(uintptr_t)15, e0 = (a0 + bytes) & ~(uintptr_t)15;
             const uint32_t D = slot_s + 128u + (uint32_t)(a0 & 15);
             if (lane == 0) {
                 mbar_arrive_expect_tx(bar_rows, (uint32_t)(e0 - b0));
-                bulk_g2s_stream(D + (uint32_t)(b0 - a0), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
+                bulk_g2s(D + (uint32_t)(b0 - a0), reinterpret_cast<const void *>(b0), (uint32_t)(e0 - b0), bar_rows);
             }
             const int hw = (int)((b0 - a0) >> 2), tw = (int)((a0 + bytes - e0) >> 2), t0 = (int)((e0 - a0) >> 2);
             if (lane >= 1 && lane - 1 < hw) cp_async_4(D + 4u * (uint32_t)(lane - 1), src + (lane - 1));
