@@ -79,6 +79,8 @@ __device__ __forceinline__ void batch_pair(int lane, int &a, int &b) {
 }
 
 // ---- the two steps of a batch, shared by phnms_select_kernel and the fused get_lanes kernel (frontend.cuh) -------------------
+// (Measured and rejected: caching each group's SECOND smallest key in a register so that most draws need no rescan -- the extra
+// compare / select per key in the key pass costs more than the rescans save: select 80 -> 92 us at the headline shape.)
 // Draw: the next (up to) kSelBatch proposals in rank order.  Lane l owns "group l" = proposals l, l + 32, ... and keeps the
 // group's smallest not-yet-drawn rank key in `gmin`; per pick one warp arg-min over the 32 group minima, then the warp
 // rescans the winning group (one key per lane) for its next minimum.  `valid(i, q)`: proposal i = g + 32 q exists.
