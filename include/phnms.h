@@ -192,8 +192,10 @@ int phnms_decode_lanes_f32(const float *rows, const int64_t *num, int64_t T, int
  * is stored at row (row0 + f) of each of the n_dst destination buffers ([rows, top_k + 1] int64).  A destination is any
  * address the current device can store to: local memory, or another GPU's buffer mapped into this process
  * (phnms_peer_open) -- then the records travel over NVLink / NVSwitch.  With every rank passing the buffers of all ranks
- * and row0 = rank * F, each rank ends up holding the records of all frames: an all-gather without a collective call
- * (one extra ~2 us launch in the same call).  Requires top_k >= 1; PHNMS_ERR_BAD_ARG unless width == top_k + 1 and
+ * and row0 = rank * F, each rank ends up holding the records of all frames: an all-gather without a collective call.
+ * On the streaming, small-frame and register-resident paths the NMS kernels store the records themselves (the select step
+ * knows keep[0 .. top_k) first; a frame the resume pass redoes is stored again); the other paths append one small record
+ * launch.  Requires top_k >= 1; PHNMS_ERR_BAD_ARG unless width == top_k + 1 and
  * row0 + F <= rows (a record is never stored outside a destination).  Completion across GPUs: phnms_peer_sync.
  */
 #define PHNMS_MAX_DST 16
@@ -203,11 +205,11 @@ typedef struct phnms_collect {
     int64_t row0;                     /* row of this call's frame 0 in every destination               */
     int64_t rows;                     /* rows of every destination: row0 + F must not exceed it        */
     int64_t *dst[PHNMS_MAX_DST];      /* device-accessible [rows, width] int64 buffers, 8-byte aligned   */
-    /* Optional completion across GPUs in the SAME launch (see phnms_peer_sync for the flag protocol): when signal_epoch or
-     * wait_epoch is non-zero, the last block of the record kernel stores signal_epoch to signal_dst[d] (d < n_dst: this
-     * rank's slot in rank d's flag array; system-scope release, after all record stores) and then waits until
-     * wait_src[r] >= wait_epoch for all r < n_dst.  sync_counter: one device uint32, zero before the first call (the kernel
-     * leaves it zero).  All zero / NULL: records only. */
+    /* Optional completion across GPUs in the SAME call (see phnms_peer_sync for the flag protocol): when signal_epoch or
+     * wait_epoch is non-zero, signal_epoch is stored to signal_dst[d] (d < n_dst: this rank's slot in rank d's flag array;
+     * system-scope release, after all record stores of the call) and wait_src[r] >= wait_epoch is awaited for all r < n_dst --
+     * by one single-block launch after the NMS kernels when they stored the records themselves, else by the last block of the
+     * record kernel.  sync_counter: one device uint32, zero before the first call (left zero).  All zero / NULL: records only. */
     uint64_t signal_epoch, wait_epoch, timeout_ns;
     uint64_t *signal_dst[PHNMS_MAX_DST];
     const uint64_t *wait_src;

@@ -228,6 +228,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  : "memory");
 }
 
+// Compact kept-lane records {keep[0 .. top_k), num_to_keep} of a frame, stored by the NMS kernels themselves into every listed
+// destination (local memory or other GPUs' buffers, then over NVLink): n == 0 switches it off.  See phnms_forward_collect_f32.
+constexpr int kMaxCollectDst = 16;   // == PHNMS_MAX_DST
+struct RecordSink {
+    int n, width;        // destinations; int64 words per record (top_k + 1)
+    long long row0;      // this call's frame f goes to row row0 + f of every destination
+    long long *dst[kMaxCollectDst];
+};
+__device__ __forceinline__ void record_store(const RecordSink &r, long long f, int c, long long v) {
+    for (int d = 0; d < r.n; ++d) r.dst[d][(r.row0 + f) * r.width + c] = v;
+}
+
 __device__ __forceinline__ void st_global_cs_u64(long long *p, long long v) {  // streaming store: outputs are write-once
     asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }

@@ -32,7 +32,6 @@ struct FusedLayout {
     int total;
 };
 
-constexpr int kMaxCollectDst = 16;   // == PHNMS_MAX_DST
 
 struct FusedParams {
     const float *props;
@@ -57,6 +56,7 @@ struct FusedParams {
     const unsigned int *frame_count; //           (the resume list of the streaming path, stream.cuh); static schedule only
     long long *trace;  // optional: CTA 0 / thread 0 writes clock64() at phase boundaries (phnms_forward_f32_trace)
     int trace_len;
+    RecordSink rec;    // optional (rec.n > 0): the register-resident kernel also stores every frame's compact record
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }

@@ -1010,7 +1010,14 @@ __global__ void __launch_bounds__(512, 1) phnms_freg_kernel(const FusedParams p,
                     if (i >= n) st_global_cs_u64(keep_f + i, 0ll);  // :139-140
                 }
             }
-            if (rank == 0 && tid == 0) p.num_keep[f] = p.top_k < n ? p.top_k : n;  // :142
+            if (rank == 0 && tid == 0) {
+                const long long num = p.top_k < n ? p.top_k : n;
+                p.num_keep[f] = num;  // :142
+                if (p.rec.n > 0) {    // the frame's compact record (keep[0 .. n) was written by this thread, or by the kernel before)
+                    for (int c = 0; c < p.rec.width - 1; ++c) record_store(p.rec, f, c, c < num ? keep_f[c] : 0ll);
+                    record_store(p.rec, f, p.rec.width - 1, num);
+                }
+            }
         }
         PHNMS_TRACE(13);  // outputs written
 

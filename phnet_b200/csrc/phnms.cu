@@ -81,7 +81,7 @@ int ensure_max_smem(const void *kern, int smem_optin) {
 
 // experiment knobs of debug sessions, read once at load (never on the call path)
 struct EnvKnobs {
-    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, no_small, small_grid_f, debug, skip, small_batch;
+    int topm_count, no_topm, select_cap, lanes_per_pass, stream_warps, stream_cpt, no_stream, no_small, small_grid_f, no_fused_records, debug, skip, small_batch;
     EnvKnobs() {
         auto geti = [](const char *n) { const char *v = getenv(n); return v ? atoi(v) : 0; };
         topm_count = geti("PHNMS_TOPM_COUNT");
@@ -92,7 +92,8 @@ struct EnvKnobs {
         stream_cpt = geti("PHNMS_STREAM_CPT");
         no_stream = getenv("PHNMS_NO_STREAM") != nullptr;
         no_small = getenv("PHNMS_NO_SMALL") != nullptr;
-        small_grid_f = getenv("PHNMS_SMALL_GRID_F") != nullptr;   // experiment: one CTA per frame instead of persistent CTAs
+        small_grid_f = getenv("PHNMS_SMALL_GRID_F") != nullptr;
+        no_fused_records = getenv("PHNMS_NO_FUSED_RECORDS") != nullptr;   // A/B: records by the separate collect kernel   // experiment: one CTA per frame instead of persistent CTAs
         debug = getenv("PHNMS_DEBUG") != nullptr;
         small_batch = getenv("PHNMS_SMALL_BATCH") ? geti("PHNMS_SMALL_BATCH") : -1;
         skip = geti("PHNMS_SKIP");   // timing experiments only (results are wrong): 1 = no select, 2 = no stream, 4 = no resume
@@ -619,7 +620,8 @@ int phnms_order_f32(const float *scores, const int32_t *n_valid, int64_t F, int6
 
 static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                         float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
-                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len);
+                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len,
+                        const RecordSink *rec = nullptr, bool *rec_done = nullptr);
 
 int phnms_forward_f32(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                       float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
@@ -647,9 +649,35 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
     if ((int64_t)collect->width != top_k + 1 || F < 0 || collect->row0 + F > collect->rows) return PHNMS_ERR_BAD_ARG;
     for (int d = 0; d < collect->n_dst; ++d)
         if (!collect->dst[d] || ((uintptr_t)collect->dst[d] & 7u)) return PHNMS_ERR_BAD_ARG;
+    RecordSink sink = {};
+    sink.n = collect->n_dst;
+    sink.width = (int)(top_k + 1);
+    sink.row0 = collect->row0;
+    for (int d = 0; d < collect->n_dst; ++d) sink.dst[d] = reinterpret_cast<long long *>(collect->dst[d]);
+    bool rec_done = false;
     int rc = forward_impl(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws,
-                          ws_bytes, tuning, stream_, nullptr, 0);
+                          ws_bytes, tuning, stream_, nullptr, 0, N > 0 ? &sink : nullptr, &rec_done);
     if (rc != PHNMS_OK || F == 0) return rc;
+    if (rec_done) {
+        // The NMS kernels stored the records themselves.  What is left is the completion across GPUs: one single-block launch
+        // (system-scope release of this rank's epoch after the kernels above, acquire of the epoch the consumer needs).
+        if (!collect->signal_epoch && !collect->wait_epoch) return PHNMS_OK;
+        if (collect->wait_epoch && !collect->wait_src) return PHNMS_ERR_BAD_ARG;
+        PeerSyncArgs a;
+        a.n = collect->n_dst;
+        a.signal_epoch = collect->signal_epoch;
+        a.wait_epoch = collect->wait_epoch;
+        a.timeout_ns = collect->timeout_ns ? collect->timeout_ns : 10000000000ull;
+        a.wait_src = reinterpret_cast<const unsigned long long *>(collect->wait_src);
+        a.status = collect->status;
+        for (int d = 0; d < kMaxCollectDst; ++d) a.signal_dst[d] = nullptr;
+        for (int d = 0; d < collect->n_dst; ++d) {
+            if (collect->signal_epoch && (!collect->signal_dst[d] || ((uintptr_t)collect->signal_dst[d] & 7u))) return PHNMS_ERR_BAD_ARG;
+            a.signal_dst[d] = reinterpret_cast<unsigned long long *>(collect->signal_dst[d]);
+        }
+        phnms_peer_sync_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(a);
+        return (int)cudaGetLastError();
+    }
     CollectArgs ca;
     ca.n = collect->n_dst;
     ca.row0 = collect->row0;
@@ -689,7 +717,7 @@ int phnms_forward_collect_f32(const float *props, const float *scores, const int
 static int launch_stream(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                          float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
                          void *ws, size_t ws_bytes, const phnms_tuning *tuning, const DeviceInfo &dev, const phnms_plan &pl,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const RecordSink &rec) {
     if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
     const phnms_tuning t = tuning ? *tuning : phnms_tuning{};
     const int P = 5 + n_off, SLOT = kHdr + 4 * ((P + 3) & ~3);
@@ -720,6 +748,7 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
         sp.flags = flags; sp.ctrs = ctrs;
         sp.keep = reinterpret_cast<long long *>(keep);
         sp.num_keep = reinterpret_cast<long long *>(num_keep);
+        sp.rec = rec;
         int warps = kSelWarps;
         while (warps > 1 && select_smem_bytes((int)N, n_off, (int)top_k, warps) > 100 * 1024) warps >>= 1;
         const size_t sm = select_smem_bytes((int)N, n_off, (int)top_k, warps);
@@ -791,6 +820,7 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
     fp.trace = nullptr; fp.trace_len = 0;
     fp.topm = nullptr; fp.topm_count = 0; fp.claim_ctr = nullptr;
     fp.frame_list = list; fp.frame_count = ctrs;
+    fp.rec = rec;   // (a frame that is redone gets its record rewritten)
     const FregLayout RL = freg_layout(rp.rows_per_cta, P, rp.cluster);
     if (n_off == 72) return fail_at("resume launch", launch_cluster(phnms_freg_kernel<72, 1, false, false>, rp, stream, fp, RL));
     if (rp.cols_per_thread == 1) return fail_at("resume launch", launch_cluster(phnms_freg_kernel<36, 1, false, false>, rp, stream, fp, RL));
@@ -799,7 +829,13 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
 
 static int forward_impl(const float *props, const float *scores, const int32_t *n_valid, int64_t F, int64_t N, int n_off,
                         float thresh, int64_t top_k, int sort_model, int64_t *keep, int64_t *num_keep, int64_t *parent,
-                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len) {
+                        void *ws, size_t ws_bytes, const phnms_tuning *tuning, void *stream_, int64_t *trace, int trace_len,
+                        const RecordSink *rec_in, bool *rec_done) {
+    // compact records: written by the kernels themselves on the paths that can (streaming, small-frame, register-resident
+    // cluster kernel); *rec_done tells the caller whether it still has to launch the separate record kernel
+    RecordSink rec = {};
+    if (rec_in && !g_env.no_fused_records && !trace) rec = *rec_in;
+    if (rec_done) *rec_done = false;
     int rc = check_shape(F, N, n_off);
     if (rc != PHNMS_OK) return rc;
     if (sort_model < 0 || sort_model > 2 || top_k < 0) return PHNMS_ERR_BAD_ARG;
@@ -832,6 +868,8 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
         q.num_keep = reinterpret_cast<long long *>(num_keep);
         q.parent = reinterpret_cast<long long *>(parent);
         q.F = F; q.top_k = top_k; q.N = (int)N; q.sort_model = sort_model; q.thr = thresh;
+        q.rec = rec;
+        if (rec_done) *rec_done = rec.n > 0;
 #define PHNMS_LAUNCH_SMALL(NO, MT, MB)                                                                                  \
     do {                                                                                                              \
         rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<NO, MT, MB>), dev.smem_optin);         \
@@ -844,9 +882,11 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
 #undef PHNMS_LAUNCH_SMALL
         return fail_at("small launch", (int)cudaGetLastError());
     }
-    if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_STREAM)
+    if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_STREAM) {
+        if (rec_done) *rec_done = rec.n > 0 && !g_env.skip;
         return launch_stream(props, scores, n_valid, F, N, n_off, thresh, top_k, sort_model, keep, num_keep, parent, ws, ws_bytes,
-                             tuning, dev, pl, stream);
+                             tuning, dev, pl, stream, rec);
+    }
 
     if (pl.path == PHNMS_PATH_FUSED) {
         FusedParams fp;
@@ -872,8 +912,11 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
         fp.claim_ctr = nullptr;
         fp.frame_list = nullptr;
         fp.frame_count = nullptr;
+        fp.rec = RecordSink{};
         if (pl.variant == PHNMS_FUSED_REG) {
             if (!ws || ws_bytes < pl.workspace_bytes) return PHNMS_ERR_WORKSPACE;
+            fp.rec = rec;
+            if (rec_done) *rec_done = rec.n > 0;
             unsigned long long *claim_ctr = reinterpret_cast<unsigned long long *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
             int *topm = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(claim_ctr) + 256);
             {   // frames are claimed dynamically by default only where that measured faster (single-CTA frames, one

@@ -48,6 +48,7 @@ struct SelectParams {
     unsigned int *ctrs;      // ctrs[0] = length of the resume list (cleared here)
     long long *keep;
     long long *num_keep;
+    RecordSink rec;          // optional (rec.n > 0): the frame's compact record {keep[0 .. top_k), num} goes to every destination
 };
 
 __host__ __device__ inline int select_warp_words(int N, int n_off, int top_k) {
@@ -323,6 +324,9 @@ __global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_selec
         sp.num_keep[f] = (long long)nk;   // :142 (nk <= top_k)
         if (open) sp.flags[f] = 0;
     }
+    // (an open frame that the resume pass redoes gets its record rewritten there)
+    if (sp.rec.n > 0 && lane < sp.rec.width)
+        record_store(sp.rec, f, lane, lane == sp.rec.width - 1 ? (long long)nk : (lane < nk ? (long long)slots[lane * slot_words + 1] : 0ll));
 }
 
 }  // namespace phnms

@@ -36,6 +36,7 @@ struct SmallParams {
     long long top_k;
     int N, sort_model;
     float thr;
+    RecordSink rec;   // optional (rec.n > 0): every frame's compact record {keep[0 .. top_k), num} goes to every destination
 };
 
 struct SmallLayout {
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
                     sts_v4(pub_s + kHdr + 16u * g, w[0], w[1], w[2], w[3]);
                 }
                 sp.keep[(size_t)f * N + nk] = (long long)(uint32_t)best;   // :118
+                if (sp.rec.n > 0 && nk < sp.rec.width - 1) record_store(sp.rec, f, (int)nk, (long long)(uint32_t)best);
             }
             __syncthreads();
             if (!stream_eval<NOFF, 1, 1>(pub_s, 1, real, myK, st, en, mb, x, sp.thr, par, (int)nk)) {
@@ -252,6 +254,10 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
             if (tid >= nk) st_global_cs_u64(sp.keep + (size_t)f * N + tid, 0ll);   // :139-140
         }
         if (tid == 0) sp.num_keep[f] = sp.top_k < nk ? sp.top_k : nk;   // :142
+        if (sp.rec.n > 0) {
+            for (long long c = nk + tid; c < sp.rec.width - 1; c += blockDim.x) record_store(sp.rec, f, (int)c, 0ll);
+            if (tid == 0) record_store(sp.rec, f, sp.rec.width - 1, sp.top_k < nk ? sp.top_k : nk);
+        }
     }
 }
 

@@ -37,6 +37,22 @@ def test_records_match_keep_and_num(cuda_device, tuning, top_k):
             assert bool((b[:row0] == -7).all()) and bool((b[row0 + F:] == -7).all()), "stores outside the call's rows"
 
 
+@pytest.mark.parametrize("top_k", [3, 4, 8])
+def test_records_of_frames_redone_by_the_resume_pass(cuda_device, top_k):
+    """The select kernel stores a record for every frame; a frame it left open (draw cap 8 here) and the streaming pass found
+    unfinished is redone by the cluster kernel, which stores the record again -- the final one must be in every buffer."""
+    dev = cuda_device
+    F, N = 400, 1000
+    props, scores = synth.make_frames(F, N, 72, seed=top_k, groups=2, outlier_frac=0.03)
+    bufs = [torch.full((F + 3, top_k + 1), -7, dtype=torch.int64, device=dev) for _ in range(2)]
+    got = nms_batched(props.to(dev), scores.to(dev), 50.0, top_k, tuning=dict(variant=3, select_cap=8), collect=peer.local_collect(bufs, 2))
+    torch.cuda.synchronize()
+    assert_same(got, oracle_batched(props, scores, 50.0, top_k), f"collect + resume top_k={top_k}")
+    want = sharding.pack_kept(got[0], got[1], top_k)
+    for b in bufs:
+        assert torch.equal(b[2:2 + F], want) and bool((b[:2] == -7).all()) and bool((b[2 + F:] == -7).all())
+
+
 def test_ragged_and_empty_frames(cuda_device):
     dev = cuda_device
     F, N = 24, 300
