@@ -126,15 +126,21 @@ def _launch_f64(boxes, scores, n_valid, F, N, n_off, overlap, top_k, keep, num, 
     top_k = int(top_k)
     if top_k < 0:
         raise TypeError("top_k must be non-negative (unsigned long in the reference, nms.cpp:48)")
-    if n_valid is not None:
-        raise RuntimeError("n_valid is not supported for float64 boxes")
     L = _capi.lib()
     dev = boxes.device
     with torch.cuda.device(dev):
+        if n_valid is not None:
+            # ragged batch: the padding sorts behind every real proposal (-inf; among equal scores torch's sort of more than 32
+            # elements is stable, so a real -inf score still precedes the padding), frame f is then ordered like
+            # `scores[f, :n_valid[f]].sort(0, True)` (frames of <= 32 real proposals: torch's unstable small sort may break ties
+            # differently on the padded row than on the slice)
+            pad = torch.arange(N, device=dev)[None, :] >= n_valid.to(torch.int64)[:, None]
+            scores = scores.reshape(F, N).masked_fill(pad, float("-inf"))
         order = scores.sort(-1, True)[1].contiguous()
         nbytes = int(L.phnms_ordered_f64_workspace_bytes(F, N))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        rc = L.phnms_forward_ordered_f64(boxes.data_ptr(), order.data_ptr(), None, F, N, n_off, float(overlap), top_k,
+        rc = L.phnms_forward_ordered_f64(boxes.data_ptr(), order.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
+                                         F, N, n_off, float(overlap), top_k,
                                          keep.data_ptr(), num.data_ptr(), parent.data_ptr(), ws.data_ptr(), nbytes,
                                          torch.cuda.current_stream(dev).cuda_stream)
         ws.record_stream(torch.cuda.current_stream(dev))

@@ -61,3 +61,24 @@ def test_cuda_f64_matches_reference_double_kernels(cuda_device):
         assert int(nb[f]) == m and np.array_equal(kb[f].cpu().numpy(), k) and np.array_equal(pb[f].cpu().numpy(), par)
     with pytest.raises(RuntimeError):
         nms(p.half(), s.half(), overlap=50, top_k=4)
+
+
+@pytest.mark.gpu
+def test_ragged_double_batches_equal_per_frame_calls(cuda_device):
+    """n_valid with float64 boxes: frame f of the batch equals the one-frame call on its first n_valid[f] rows (that call is what
+    the fixtures above pin against the reference's nms_kernel<double>)."""
+    import torch
+    from phnet_b200 import synth
+    from phnet_b200.ops import nms, nms_batched
+    F, N = 7, 150
+    for n_off in (72, 36):
+        props, scores = synth.make_frames(F, N, n_off, seed=5 + n_off, groups=3)
+        p, s = props.double().to(cuda_device), scores.double().to(cuda_device)
+        n_valid = torch.tensor([150, 0, 1, 40, 33, 149, 77], dtype=torch.int32, device=cuda_device)
+        keep, num, parent = nms_batched(p, s, 50.0, 4, n_valid)
+        for f in range(F):
+            n = int(n_valid[f])
+            k1, n1, p1 = nms(p[f, :n].contiguous(), s[f, :n].contiguous(), 50.0, 4)
+            assert int(num[f]) == int(n1), f"frame {f}"
+            assert torch.equal(keep[f, :n], k1) and torch.equal(parent[f, :n], p1), f"frame {f}"
+            assert bool((keep[f, n:] == 0).all()) and bool((parent[f, n:] == 0).all())
