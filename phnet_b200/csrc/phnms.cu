@@ -772,6 +772,9 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
         q.off_ring = ss.L.off_ring; q.off_slots = ss.L.off_slots; q.slot_bytes = ss.L.slot_bytes; q.off_bit = ss.L.off_bit;
         const int lanes = ss.lanes;
         int rc = 0;
+// (Measured and rejected: launching the streaming kernel with programmatic stream serialization -- griddepcontrol.launch_dependents at
+// the top of the select kernel, griddepcontrol.wait before the first kept-block request -- so that its prologue overlaps the select
+// kernel's tail: 0.835 -> 0.724 of the roofline at the headline shape, no effect at 36 offsets.)
 #define PHNMS_LAUNCH_STREAM(NO, NK, GE)                                                                               \
     do {                                                                                                              \
         rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_stream_kernel<NO, NK, GE>), dev.smem_optin);        \
