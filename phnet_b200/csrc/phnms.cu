@@ -871,18 +871,23 @@ static int forward_impl(const float *props, const float *scores, const int32_t *
         q.num_keep = reinterpret_cast<long long *>(num_keep);
         q.parent = reinterpret_cast<long long *>(parent);
         q.F = F; q.top_k = top_k; q.N = (int)N; q.sort_model = sort_model; q.thr = thresh;
-        q.rec = rec;
         if (rec_done) *rec_done = rec.n > 0;
+#define PHNMS_LAUNCH_SMALL_R(NO, MT, MB, RE)                                                                            \
+    do {                                                                                                              \
+        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<NO, MT, MB, RE>), dev.smem_optin);     \
+        if (rc) return fail_at("small smem attribute", rc);                                                           \
+        phnms_small_kernel<NO, MT, MB, RE><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q, rec); \
+    } while (0)
 #define PHNMS_LAUNCH_SMALL(NO, MT, MB)                                                                                  \
     do {                                                                                                              \
-        rc = ensure_max_smem(reinterpret_cast<const void *>(phnms_small_kernel<NO, MT, MB>), dev.smem_optin);         \
-        if (rc) return fail_at("small smem attribute", rc);                                                           \
-        phnms_small_kernel<NO, MT, MB><<<(unsigned)pl.grid, pl.threads, (size_t)pl.smem_bytes, stream>>>(q);          \
+        if (rec.n > 0) PHNMS_LAUNCH_SMALL_R(NO, MT, MB, true);                                                        \
+        else PHNMS_LAUNCH_SMALL_R(NO, MT, MB, false);                                                                 \
     } while (0)
         if (n_off == 72) PHNMS_LAUNCH_SMALL(72, 512, 1);
         else if (pl.threads <= 256) PHNMS_LAUNCH_SMALL(36, 256, 3);
         else PHNMS_LAUNCH_SMALL(36, 512, 1);
 #undef PHNMS_LAUNCH_SMALL
+#undef PHNMS_LAUNCH_SMALL_R
         return fail_at("small launch", (int)cudaGetLastError());
     }
     if (pl.path == PHNMS_PATH_FUSED && pl.variant == PHNMS_FUSED_STREAM) {

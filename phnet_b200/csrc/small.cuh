@@ -36,7 +36,6 @@ struct SmallParams {
     long long top_k;
     int N, sort_model;
     float thr;
-    RecordSink rec;   // optional (rec.n > 0): every frame's compact record {keep[0 .. top_k), num} goes to every destination
 };
 
 struct SmallLayout {
@@ -96,8 +95,10 @@ __device__ __forceinline__ void small_request(const SmallParams &sp, long long f
 // MAXT / MINB: launch bounds (frames of <= 256 proposals at 36 offsets fit three CTAs per SM in 80 registers).
 // Persistent: CTA b takes frames b, b + gridDim.x, ...; a warp requests its rows of the NEXT frame as soon as the current ones are
 // in registers, so the load of a frame overlaps the greedy rounds of the one before.
-template <int NOFF, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallParams sp) {
+// REC: also store every frame's compact record (`rec`: {keep[0 .. top_k), num} to every destination) -- a separate instantiation, the plain one carries none of it (the kernel
+// sits at its register limit: the branches alone cost 2 %).
+template <int NOFF, int MAXT, int MINB, bool REC>
+__global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallParams sp, const RecordSink rec) {
     constexpr int P = 5 + NOFF, MW = (P + 31) / 32, P4 = (P + 3) & ~3, SLOT = kHdr + 4 * P4;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
         // Keys and the published slot are double buffered and the parity flips after EVERY round, also the last one of a frame:
         // what a round writes was last read two rounds earlier, with a barrier in between.
         bool alive = real[0];
-        long long nk = 0;
+        int nk = 0;
         while (n > 0) {
             const u64 wm = warp_min_u64(alive ? myK[0] : kNone64);
             if (lane == 0) wmin[parity * 16 + warp] = wm;
@@ -231,10 +232,10 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
                     sts_v4(pub_s + kHdr + 16u * g, w[0], w[1], w[2], w[3]);
                 }
                 sp.keep[(size_t)f * N + nk] = (long long)(uint32_t)best;   // :118
-                if (sp.rec.n > 0 && nk < sp.rec.width - 1) record_store(sp.rec, f, (int)nk, (long long)(uint32_t)best);
+                if (REC && nk < rec.width - 1) record_store(rec, f, nk, (long long)(uint32_t)best);
             }
             __syncthreads();
-            if (!stream_eval<NOFF, 1, 1>(pub_s, 1, real, myK, st, en, mb, x, sp.thr, par, (int)nk)) {
+            if (!stream_eval<NOFF, 1, 1>(pub_s, 1, real, myK, st, en, mb, x, sp.thr, par, nk)) {
                 // a pair with a negative common start somewhere in the warp (header words / the wrapped unsigned-char counter, :38)
                 FusedParams fp;
                 fp.thr = sp.thr;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
             }
             if (par[0] == (uint32_t)(nk + 1)) alive = false;   // covered by this lane (:120-122), or the lane itself
             ++nk;
-            if (nk == sp.top_k) break;    // :133
+            if ((long long)nk == sp.top_k) break;    // :133
         }
 
         // ---- 3. outputs -------------------------------------------------------------------------------------------------------------
@@ -253,10 +254,10 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
             st_global_cs_u64(sp.parent + (size_t)f * N + tid, (long long)par[0]);
             if (tid >= nk) st_global_cs_u64(sp.keep + (size_t)f * N + tid, 0ll);   // :139-140
         }
-        if (tid == 0) sp.num_keep[f] = sp.top_k < nk ? sp.top_k : nk;   // :142
-        if (sp.rec.n > 0) {
-            for (long long c = nk + tid; c < sp.rec.width - 1; c += blockDim.x) record_store(sp.rec, f, (int)c, 0ll);
-            if (tid == 0) record_store(sp.rec, f, sp.rec.width - 1, sp.top_k < nk ? sp.top_k : nk);
+        if (tid == 0) sp.num_keep[f] = sp.top_k < (long long)nk ? sp.top_k : (long long)nk;   // :142
+        if (REC) {
+            for (int c = nk + tid; c < rec.width - 1; c += (int)blockDim.x) record_store(rec, f, c, 0ll);
+            if (tid == 0) record_store(rec, f, rec.width - 1, sp.top_k < (long long)nk ? sp.top_k : (long long)nk);
         }
     }
 }
