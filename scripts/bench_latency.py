@@ -52,6 +52,19 @@ def main():
                 fn(ps[f], ss[f], 50.0, top_k)
             torch.cuda.synchronize()
             out[f"{name}_N{N}_No{n_off}_k{top_k}_async_presliced_calls_per_s"] = round(F / (time.perf_counter() - t0), 1)
+            if name == "ours":      # CUDA-graph replay for the fixed shape: with the two input copies, and the replay alone
+                from phnet_b200.ops import GraphedNMS
+                g = GraphedNMS(N, n_off, 50.0, top_k, device=dev)
+                for mode in ("copy+replay", "replay"):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for f in range(F):
+                        if mode == "replay":
+                            g.replay()
+                        else:
+                            g(ps[f], ss[f])
+                    torch.cuda.synchronize()
+                    out[f"graph_N{N}_No{n_off}_k{top_k}_{mode}_calls_per_s"] = round(F / (time.perf_counter() - t0), 1)
     print(json.dumps(out))
 
 

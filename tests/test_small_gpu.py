@@ -143,3 +143,27 @@ def test_subnormal_offsets_and_thresholds(cuda_device):
         props, scores = synth.make_frames(6, 240, n_off, seed=12, groups=3)
         for thr in (10.0, 20.0, 30.0, 40.0, 50.0):
             run_both(props, scores, thr, 4, cuda_device, ctx=f"No={n_off} thr={thr}")
+
+
+def test_graph_replay_of_the_one_frame_call(cuda_device):
+    """GraphedNMS: the captured launch, replayed on new contents of its static buffers, equals the eager call -- fixed-size frames,
+    ragged frames (n_valid inside the graph), and a frame of more than 512 proposals (the cluster kernel with its workspace)."""
+    from phnet_b200.ops import GraphedNMS
+    for N, n_off, top_k in ((240, 72, 4), (240, 36, 8), (1000, 72, 4)):
+        props, scores = synth.make_frames(6, N, n_off, seed=N + top_k, groups=3)
+        p, s = props.to(cuda_device), scores.to(cuda_device)
+        g = GraphedNMS(N, n_off, 50.0, top_k, device=cuda_device)
+        for f in range(6):
+            keep, num, parent = g(p[f], s[f])
+            want = nms(p[f], s[f], 50.0, top_k)
+            assert torch.equal(keep, want[0]) and int(num) == int(want[1]) and torch.equal(parent, want[2]), f"N={N} f={f}"
+        g.boxes.copy_(p[0]); g.scores.copy_(s[0])             # the caller filled the static buffers itself
+        keep, num, parent = g.replay()
+        assert torch.equal(keep, nms(p[0], s[0], 50.0, top_k)[0])
+        if N <= 512:
+            r = GraphedNMS(N, n_off, 50.0, top_k, device=cuda_device, ragged=True)
+            for n in (N, 1, 33, 100, 0):
+                keep, num, parent = r(p[1, :n].contiguous(), s[1, :n].contiguous())
+                want = nms(p[1, :n].contiguous(), s[1, :n].contiguous(), 50.0, top_k)
+                assert int(num) == int(want[1]) and torch.equal(keep[:n], want[0]) and torch.equal(parent[:n], want[2]), f"ragged n={n}"
+                assert bool((keep[n:] == 0).all()) and bool((parent[n:] == 0).all())
