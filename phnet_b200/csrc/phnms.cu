@@ -748,15 +748,19 @@ static int launch_stream(const float *props, const float *scores, const int32_t 
         sp.flags = flags; sp.ctrs = ctrs;
         sp.keep = reinterpret_cast<long long *>(keep);
         sp.num_keep = reinterpret_cast<long long *>(num_keep);
-        sp.rec = rec;
         int warps = kSelWarps;
         while (warps > 1 && select_smem_bytes((int)N, n_off, (int)top_k, warps) > 100 * 1024) warps >>= 1;
         const size_t sm = select_smem_bytes((int)N, n_off, (int)top_k, warps);
-        {   // (static + dynamic shared memory beyond 48 KB needs the opt-in; cached per device, so simply always)
-            const int e2 = ensure_max_smem(reinterpret_cast<const void *>(phnms_select_kernel), dev.smem_optin);
+        // (static + dynamic shared memory beyond 48 KB needs the opt-in; cached per device, so simply always)
+        if (rec.n > 0) {
+            const int e2 = ensure_max_smem(reinterpret_cast<const void *>(phnms_select_kernel<true>), dev.smem_optin);
             if (e2) return fail_at("select smem attribute", e2);
+            phnms_select_kernel<true><<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(sp, rec);
+        } else {
+            const int e2 = ensure_max_smem(reinterpret_cast<const void *>(phnms_select_kernel<false>), dev.smem_optin);
+            if (e2) return fail_at("select smem attribute", e2);
+            phnms_select_kernel<false><<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(sp, rec);
         }
-        phnms_select_kernel<<<(unsigned)((F + warps - 1) / warps), warps * 32, sm, stream>>>(sp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail_at("select launch", (int)e);
     }

@@ -48,7 +48,6 @@ struct SelectParams {
     unsigned int *ctrs;      // ctrs[0] = length of the resume list (cleared here)
     long long *keep;
     long long *num_keep;
-    RecordSink rec;          // optional (rec.n > 0): the frame's compact record {keep[0 .. top_k), num} goes to every destination
 };
 
 __host__ __device__ inline int select_warp_words(int N, int n_off, int top_k) {
@@ -169,7 +168,10 @@ __device__ __forceinline__ int select_scan_batch(int nb, u64 myc, int nk, int to
     return nk;
 }
 
-__global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_select_kernel(const SelectParams sp) {
+// REC: also store every frame's compact record {keep[0 .. top_k), num} to every destination of `rec` (phnms_forward_collect_f32).  A
+// template parameter and a separate argument: carrying the descriptor inside SelectParams cost the plain kernel 7 % (80 -> 86 us).
+template <bool REC>
+__global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_select_kernel(const SelectParams sp, const RecordSink rec) {
     extern __shared__ __align__(16) unsigned char smem_sel[];
     __shared__ float bit_key[kSelWarps][32];
     __shared__ int bit_val[kSelWarps][32];
@@ -325,8 +327,8 @@ __global__ void __launch_bounds__(kSelWarps * 32, PHNMS_SELECT_CTAS) phnms_selec
         if (open) sp.flags[f] = 0;
     }
     // (an open frame that the resume pass redoes gets its record rewritten there)
-    if (sp.rec.n > 0 && lane < sp.rec.width)
-        record_store(sp.rec, f, lane, lane == sp.rec.width - 1 ? (long long)nk : (lane < nk ? (long long)slots[lane * slot_words + 1] : 0ll));
+    if (REC && lane < rec.width)
+        record_store(rec, f, lane, lane == rec.width - 1 ? (long long)nk : (lane < nk ? (long long)slots[lane * slot_words + 1] : 0ll));
 }
 
 }  // namespace phnms
