@@ -92,7 +92,9 @@ __device__ __forceinline__ void small_request(const SmallParams &sp, long long f
     cp_async_mbar_arrive_noinc(bar);
 }
 
-// MAXT / MINB: launch bounds (frames of <= 256 proposals at 36 offsets fit three CTAs per SM in 80 registers).
+// MAXT / MINB: launch bounds (frames of <= 256 proposals at 36 offsets fit three CTAs per SM in 80 registers).  (Measured and
+// rejected: two proposals per thread at 36 offsets -- four warps per 240-proposal frame, two chains per thread: 0.344 vs 0.354 of the
+// roofline at top_k 8, 0.570 vs 0.583 at top_k 4.)
 // Persistent: CTA b takes frames b, b + gridDim.x, ...; a warp requests its rows of the NEXT frame as soon as the current ones are
 // in registers, so the load of a frame overlaps the greedy rounds of the one before.
 // REC: also store every frame's compact record (`rec`: {keep[0 .. top_k), num} to every destination) -- a separate instantiation, the plain one carries none of it (the kernel
