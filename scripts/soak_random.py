@@ -2,6 +2,7 @@
 threshold, generator (lane groups, outliers, ties), ragged n_valid, device algorithm (auto / streaming with random warps, lanes
 per pass and draw cap / the one-launch small-frame kernel with random grids / cluster kernels with random cluster size and schedule / tiled), stream -- each checked bit for bit
 against the CPU oracle on a sample of its frames, and every configuration launched three times in a row with identical results.
+Every third configuration also collects the compact kept-lane records and checks them.
 A hang becomes a failed launch (mbarrier waits are bounded, common.cuh), a race a mismatch.  Prints one line per 500 launches.
 
     ITER=10000 SEED=0 python scripts/soak_random.py
@@ -9,7 +10,7 @@ A hang becomes a failed launch (mbarrier waits are bounded, common.cuh), a race 
 import os, random, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from phnet_b200 import _capi, synth
+from phnet_b200 import _capi, peer, sharding, synth
 from phnet_b200.ops import nms_batched
 from tests.util import assert_same, oracle_batched
 
@@ -56,22 +57,33 @@ while launches < iters:
         nv = torch.randint(0, N + 1, (F,), generator=torch.Generator().manual_seed(rng.randrange(1 << 30)), dtype=torch.int32).to(dev)
     ctx = f"F={F} N={N} No={n_off} top_k={top_k} thr={thr} groups={groups} outl={outl} ties={ties} ragged={nv is not None} tune={tune}"
     use_side = rng.random() < 0.3
+    # every third configuration also collects the compact kept-lane records (stored by the NMS kernels themselves on the
+    # streaming / small-frame / cluster paths, by the record kernel elsewhere) into two local buffers at a random row offset
+    bufs, row0 = None, 0
+    if top_k >= 1 and top_k <= 64 and rng.random() < 0.33:
+        row0 = rng.choice([0, 3])
+        bufs = [torch.full((F + row0 + 2, top_k + 1), -7, dtype=torch.int64, device=dev) for _ in range(2)]
     outs = []
     try:
         for _ in range(3):
             if use_side:
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    outs.append(nms_batched(props, scores, thr, top_k, nv, tuning=tune))
+                    outs.append(nms_batched(props, scores, thr, top_k, nv, tuning=tune, collect=None if bufs is None else peer.local_collect(bufs, row0)))
                 torch.cuda.current_stream().wait_stream(side)
             else:
-                outs.append(nms_batched(props, scores, thr, top_k, nv, tuning=tune))
+                outs.append(nms_batched(props, scores, thr, top_k, nv, tuning=tune, collect=None if bufs is None else peer.local_collect(bufs, row0)))
         torch.cuda.synchronize()
     except Exception as e:   # noqa: BLE001
         print("FAILED LAUNCH:", ctx, repr(e), flush=True)
         raise
     for o in outs[1:]:
         assert all(torch.equal(a, b) for a, b in zip(o, outs[0])), "repeat differs: " + ctx
+    if bufs is not None:
+        want_rec = sharding.pack_kept(outs[0][0], outs[0][1], top_k)
+        for b in bufs:
+            assert torch.equal(b[row0:row0 + F], want_rec), "records differ: " + ctx
+            assert bool((b[:row0] == -7).all()) and bool((b[row0 + F:] == -7).all()), "records outside the call's rows: " + ctx
     idx = torch.arange(0, F, max(1, F // 12))[:12]
     want = oracle_batched(props[idx].cpu(), scores[idx].cpu(), thr, top_k, None if nv is None else nv[idx].cpu())
     assert_same([t[idx] for t in outs[0]], want, ctx)
