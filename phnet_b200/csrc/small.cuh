@@ -39,10 +39,10 @@ struct SmallParams {
 };
 
 struct SmallLayout {
-    int off_wmin, off_bit, off_pub, off_stash, off_slots, slot_bytes, total;
+    int off_wmin, off_bit, off_pub, off_kept, off_stash, off_slots, slot_bytes, total;
 };
 
-// shared memory: [0,128) one mbarrier per warp | wmin[2][16] u64 | bitonic scratch | 2 published slots | header stash
+// shared memory: [0,128) one mbarrier per warp | wmin[2][16] u64 | bitonic scratch | 2 published slots | kept indices | header stash
 // (5 words per thread) | per-warp staging
 __host__ __device__ inline SmallLayout small_layout(int warps, int P) {
     SmallLayout L;
@@ -54,6 +54,8 @@ __host__ __device__ inline SmallLayout small_layout(int warps, int P) {
     o += 384;
     L.off_pub = o;
     o += 2 * (kHdr + 4 * P4);
+    L.off_kept = o;          // indices of the lanes kept so far (read back when the frame's record is stored)
+    o += kSmallMaxN * 4;
     L.off_stash = o;
     o += warps * 32 * 5 * 4;
     o = (o + 127) & ~127;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
     const uint32_t slot_s = smem_s + (uint32_t)L.off_slots + (uint32_t)warp * (uint32_t)L.slot_bytes;
     u64 *wmin = reinterpret_cast<u64 *>(smem + L.off_wmin);
     uint32_t *stash = reinterpret_cast<uint32_t *>(smem + L.off_stash);
+    uint32_t *kept = reinterpret_cast<uint32_t *>(smem + L.off_kept);
     const int N = sp.N, r0 = warp * 32;
     auto rows_of = [&](long long f) {
         int n = N;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
                     sts_v4(pub_s + kHdr + 16u * g, w[0], w[1], w[2], w[3]);
                 }
                 sp.keep[(size_t)f * N + nk] = (long long)(uint32_t)best;   // :118
-                if (REC && nk < rec.width - 1) record_store(rec, f, nk, (long long)(uint32_t)best);
+                if (REC) kept[nk] = (uint32_t)best;   // (the record goes out at the end of the frame, off the rounds' critical path)
             }
             __syncthreads();
             if (!stream_eval<NOFF, 1, 1>(pub_s, 1, real, myK, st, en, mb, x, sp.thr, par, nk)) {
@@ -257,9 +260,13 @@ __global__ void __launch_bounds__(MAXT, MINB) phnms_small_kernel(const SmallPara
             if (tid >= nk) st_global_cs_u64(sp.keep + (size_t)f * N + tid, 0ll);   // :139-140
         }
         if (tid == 0) sp.num_keep[f] = sp.top_k < (long long)nk ? sp.top_k : (long long)nk;   // :142
-        if (REC) {
-            for (int c = nk + tid; c < rec.width - 1; c += (int)blockDim.x) record_store(rec, f, c, 0ll);
-            if (tid == 0) record_store(rec, f, rec.width - 1, sp.top_k < (long long)nk ? sp.top_k : (long long)nk);
+        if (REC) {   // {keep[0 .. top_k), num} to every destination, one (column, destination) pair per thread
+            const int w = rec.width;
+            for (int i = tid; i < w * rec.n; i += (int)blockDim.x) {
+                const int d = i / w, c = i - d * w;
+                const long long v = c == w - 1 ? (sp.top_k < (long long)nk ? sp.top_k : (long long)nk) : (c < nk ? (long long)kept[c] : 0ll);
+                rec.dst[d][(rec.row0 + f) * w + c] = v;
+            }
         }
     }
 }
